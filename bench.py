@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline measurement of BASELINE.json on B200.
+
+A "step" is one pass of the hot path over one batch of synthetic stripes:
+  default workload  = BASELINE config C2: RS(12,4) encode + fused CRC32-IEEE of all 16 shards,
+                      4 MiB blobs (shard 349,526 B, HBM pitch 349,568 B), 1024 stripes per GPU.
+  --workload reconstruct = config C3: same stripes, 3 random erasures per stripe.
+`value`  = device-resident whole-job data throughput (k*S*stripes / t), inputs already in HBM.
+`e2e`    = the same metric through the C-ABI host entry point cubeec_encode_contig on pinned HOST
+           buffers (H2D of the data shards and D2H of parity + CRCs inside the timed region).
+`roofline` = algorithmic bytes ((k+m)*S per stripe for encode, (k+e)*S for reconstruct) / device time
+           against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` = the oracle's multi-threaded SIMD port (AVX2 nibble tables / GFNI as klauspost would
+           select, + PCLMUL CRC32) on this box's host cores, bounded sample.
+
+python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run)
+python bench.py --impl reference ...                   (the reference's CPU path = oracle port; rank 0 only)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, M = 12, 4
+BLOB = 4 << 20
+GIB = float(1 << 30)
+
+
+def shard_size(blob, k, min_shard=2048):
+    return max((blob + k - 1) // k, min_shard)   # blobstore/common/ec/buf.go:77-81
+
+
+def measured_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(workload, stripes_sample, target_seconds=12.0):
+    """Oracle SIMD port on the host cores (bounded sample).  Returns (GiB/s of data, dict)."""
+    from oracle import pyoracle
+    S = shard_size(BLOB, K)
+    n = K + M
+    rs = pyoracle.RS(K, M)
+    rng = np.random.default_rng(0xC0BEF5)
+    buf = rng.integers(0, 256, (stripes_sample, n, S), dtype=np.uint8)
+    cores = os.cpu_count() or 1
+    crc = np.zeros((stripes_sample, n), dtype=np.uint32)
+    present = np.ones((stripes_sample, n), dtype=np.uint8)
+    if workload == "reconstruct":
+        rs.encode_batch_simd(buf, S, S, n * S, stripes_sample, threads=cores)
+        for s in range(stripes_sample):
+            present[s, rng.choice(n, size=3, replace=False)] = 0
+
+    def one():
+        if workload == "encode":
+            rs.encode_batch_simd(buf, S, S, n * S, stripes_sample, threads=cores, crc_out=crc)
+        else:
+            rs.reconstruct_batch_simd(buf, S, S, n * S, stripes_sample, present, threads=cores)
+
+    one()
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        one()
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= target_seconds or reps >= 200:
+            break
+    gibs = K * S * stripes_sample * reps / el / GIB
+    info = {"value": round(gibs, 3), "unit": "GiB/s", "cores": cores, "kind": "port",
+            "sample": f"{stripes_sample} stripes x {reps} passes, {el:.1f} s, oracle SIMD port "
+                      f"({rs.simd_kind()} GF kernels as klauspost v1.11.7 selects for k={K}; PCLMUL CRC32-IEEE), "
+                      f"one stripe per thread over all cores"}
+    return gibs, info, el / reps
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Go
+    (no toolchain here), so this is the oracle's SIMD port on all host cores; rank 0 only."""
+    if rank != 0:
+        return
+    sample = args.cpu_stripes
+    steps_s = []
+    # each "step" is one pass over the bounded sample
+    from oracle import pyoracle
+    S = shard_size(BLOB, K)
+    n = K + M
+    rs = pyoracle.RS(K, M)
+    rng = np.random.default_rng(0xC0BEF5)
+    buf = rng.integers(0, 256, (sample, n, S), dtype=np.uint8)
+    cores = os.cpu_count() or 1
+    crc = np.zeros((sample, n), dtype=np.uint32)
+    present = np.ones((sample, n), dtype=np.uint8)
+    if args.workload == "reconstruct":
+        rs.encode_batch_simd(buf, S, S, n * S, sample, threads=cores)
+        for s in range(sample):
+            present[s, rng.choice(n, size=3, replace=False)] = 0
+
+    def one():
+        if args.workload == "encode":
+            rs.encode_batch_simd(buf, S, S, n * S, sample, threads=cores, crc_out=crc)
+        else:
+            rs.reconstruct_batch_simd(buf, S, S, n * S, sample, present, threads=cores)
+
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    el = time.perf_counter() - t0
+    gibs = K * S * sample * args.steps / el / GIB
+    line = base_line(args, world, gibs, el / args.steps * 1e3)
+    line["impl"] = "reference"
+    line["n_gpus"] = args.gpus
+    line["cpu_baseline"] = {"value": round(gibs, 3), "unit": "GiB/s", "cores": cores, "kind": "port",
+                            "sample": f"{sample} stripes per step, oracle SIMD port ({rs.simd_kind()}), all cores"}
+    line["e2e"] = {"value": round(gibs, 3), "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    line["gpu_launches"] = 0
+    line["config"]["stripes_per_step"] = sample
+    print(json.dumps(line), flush=True)
+
+
+def base_line(args, world, value, ms_per_step):
+    S = shard_size(BLOB, K)
+    name = "rs_12_4_encode_crc32_data_GiB_per_s" if args.workload == "encode" else "rs_12_4_reconstruct_3erasures_data_GiB_per_s"
+    return {
+        "metric": name, "value": round(value, 3), "unit": "GiB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": ("C2: RS(12,4) encode + fused CRC32-IEEE, 4 MiB blobs" if args.workload == "encode"
+                                else "C3: RS(12,4) reconstruct, 3 random erasures per stripe, 4 MiB blobs"),
+                   "k": K, "m": M, "shard_bytes": S, "stripes_per_gpu": args.stripes, "crc": bool(args.crc),
+                   "l2": "inputs (5.7 GB per GPU) larger than the 126 MB L2; no reuse between steps",
+                   "parallelism": f"stripes partitioned over {world} GPU(s), no data-path collective"},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="encode", choices=["encode", "reconstruct"])
+    ap.add_argument("--stripes", type=int, default=1024, help="stripes per GPU per step")
+    ap.add_argument("--crc", type=int, default=1, help="fused CRC32 in the encode step (C2 asks for it)")
+    ap.add_argument("--cpu-stripes", type=int, default=128, help="stripes in the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import cubefs_b200 as cb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: cubefs_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cb.init([local_rank])
+
+    # coding matrix: built on rank 0, NCCL-broadcast to the other ranks (the only shared state)
+    if rank == 0:
+        eng0 = cb.RSEngine(K, M)
+        rows = torch.from_numpy(eng0.matrix[K:].copy()).to(dev)
+    else:
+        rows = torch.zeros((M, K), dtype=torch.uint8, device=dev)
+    if world > 1:
+        dist.broadcast(rows, src=0)
+    eng = cb.RSEngine(K, M, parity_rows=rows.cpu().numpy())
+
+    S = shard_size(BLOB, K)
+    P = (S + 127) // 128 * 128
+    n = K + M
+    ns = args.stripes
+    g = torch.Generator(device=dev).manual_seed(0xC0BEF5 + rank)
+    batch = torch.empty((ns, n, P), dtype=torch.uint8, device=dev)
+    for s0 in range(0, ns, 64):
+        batch[s0:s0 + 64] = torch.randint(0, 256, batch[s0:s0 + 64].shape, dtype=torch.uint8, device=dev, generator=g)
+    dcrc = torch.zeros(ns * n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    rng = np.random.default_rng(0xC0BEF5 + rank)
+    present = np.ones((ns, n), dtype=np.uint8)
+    erasures = 0
+    if args.workload == "reconstruct":
+        eng.dev_encode(batch.data_ptr(), S, P, n * P, ns, stream=stream, device=local_rank)
+        for s in range(ns):
+            present[s, rng.choice(n, size=3, replace=False)] = 0
+        erasures = 3
+
+    def step():
+        if args.workload == "encode":
+            eng.dev_encode(batch.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr() if args.crc else 0,
+                           stream=stream, device=local_rank)
+        else:
+            eng.dev_reconstruct(batch.data_ptr(), S, P, n * P, ns, present, stream=stream, device=local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = cb.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = cb.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_step = ms / args.steps
+    value = K * S * ns * world / (ms_step * 1e-3) / GIB
+
+    # ---- end to end through the host entry point (pinned host buffers) ----
+    e2e = None
+    if not args.no_e2e and args.workload == "encode":
+        ns_e = min(ns, 256)
+        host = torch.empty((ns_e, n * S), dtype=torch.uint8).pin_memory()
+        host.copy_(torch.randint(0, 256, host.shape, dtype=torch.uint8))
+        hnp = host.numpy()
+        for _ in range(2):
+            eng.encode_contig(hnp, S, ns_e, n * S, crc=bool(args.crc))
+        barrier()
+        t0 = time.perf_counter()
+        reps = max(2, min(args.steps, 5))
+        for _ in range(reps):
+            eng.encode_contig(hnp, S, ns_e, n * S, crc=bool(args.crc))
+        torch.cuda.synchronize(dev)
+        el = time.perf_counter() - t0
+        t = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el = float(t.item())
+        e2e = {"value": round(K * S * ns_e * world * reps / el / GIB, 3), "unit": "GiB/s",
+               "h2d_bytes_per_step": K * S * ns_e, "d2h_bytes_per_step": M * S * ns_e + (n * ns_e * 4 if args.crc else 0),
+               "stripes_per_step": ns_e, "api": "cubeec_encode_contig (pinned host ec.Buffer layout, H2D+kernel+D2H pipelined)"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg = ((K + M) if args.workload == "encode" else (K + erasures)) * S * ns
+        achieved = alg / (ms_step * 1e-3) / 1e9
+        line = base_line(args, world, value, ms_step)
+        line["clocks"] = clocks
+        line["gpu_launches"] = int(launches)
+        line["kernel"] = cb.last_kernel()
+        line["roofline"] = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": alg,
+                            "note": "per-GPU figure; device time of one step (coding kernel + CRC finalize) by CUDA events"}
+        line["e2e"] = e2e
+        if world == 1 and not args.no_cpu:
+            _, info, _ = cpu_baseline(args.workload, args.cpu_stripes)
+            line["cpu_baseline"] = info
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,14 @@
+"""cubefs_b200 -- B200-native erasure-coding + shard-checksum engine for CubeFS BlobStore.
+
+The product is the C-ABI library ``cubefs_b200/lib/libcubeec.so`` (include/cubeec.h); this
+package is the Python host-side binding used by tests and bench.py:
+
+  cubefs_b200.engine    ctypes binding of the C-ABI (RSEngine, crc32, device-resident calls)
+  cubefs_b200.codemode  mirror of blobstore/common/codemode (tactics, LRC layout)
+  cubefs_b200.ec        mirror of blobstore/common/ec (Encoder / LrcEncoder / Buffer sizes)
+  cubefs_b200.crc32block mirror of blobstore/common/crc32block framing on GPU block CRCs
+
+There is no CPU compute path: importing works anywhere, calling needs a CUDA device.
+"""
+from .engine import (CubeecError, RSEngine, crc32, crc32_blocks, device_count, init, kernel_launches,  # noqa: F401
+                     last_kernel, lib_path, load)

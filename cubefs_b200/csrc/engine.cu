@@ -1,0 +1,1122 @@
+// engine.cu -- host side of libcubeec behind the C-ABI in include/cubeec.h.
+//
+// Mirrors the call contract of klauspost/reedsolomon's Encoder as CubeFS uses it
+// (blobstore/common/ec/encoder.go:118,122,136,143,150) and adds batched / device-resident
+// entry points.  No CPU compute path exists here: every coding or checksum byte is produced by
+// the CUDA kernels in kernels.cu / bitslice.cu; without a device the calls fail.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/cubeec.h"
+#include "gfmath.h"
+#include "kernels.cuh"
+
+using namespace cbe;
+
+// ------------------------------------------------------------------------------------------
+// errors / counters
+// ------------------------------------------------------------------------------------------
+static thread_local std::string t_last_error;
+static thread_local const char* t_last_kernel = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int cuda_fail(cudaError_t e, const char* what) {
+  t_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? CUBEEC_ERR_NO_DEVICE : CUBEEC_ERR_CUDA;
+}
+#define CU(call)                                        \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+extern "C" const char* cubeec_strerror(int code) {
+  switch (code) {
+    case CUBEEC_OK: return "ok";
+    case CUBEEC_ERR_INV_SHARD_NUM: return "cannot create Encoder with less than one data shard or less than zero parity shards";
+    case CUBEEC_ERR_MAX_SHARD_NUM: return "cannot create Encoder with more than 256 data+parity shards";
+    case CUBEEC_ERR_TOO_FEW_SHARDS: return "too few shards given";
+    case CUBEEC_ERR_SHARD_NO_DATA: return "no shard data";
+    case CUBEEC_ERR_SHARD_SIZE: return "shard sizes do not match";
+    case CUBEEC_ERR_SHORT_DATA: return "not enough data to fill the number of requested shards";
+    case CUBEEC_ERR_RECONSTRUCT_REQUIRED: return "reconstruction required as one or more required data shards are nil";
+    case CUBEEC_ERR_SINGULAR: return "matrix is singular";
+    case CUBEEC_ERR_INVALID_ARG: return "invalid argument";
+    case CUBEEC_ERR_NO_DEVICE: return "no usable CUDA device (libcubeec has no CPU fallback)";
+    case CUBEEC_ERR_CUDA: return "CUDA error";
+    case CUBEEC_ERR_UNSUPPORTED: return "unsupported geometry";
+  }
+  return "unknown error";
+}
+extern "C" const char* cubeec_last_error(void) { return t_last_error.c_str(); }
+extern "C" uint64_t cubeec_kernel_launches(void) { return g_launches.load(); }
+extern "C" const char* cubeec_last_kernel(void) { return t_last_kernel; }
+
+// ------------------------------------------------------------------------------------------
+// per-device context
+// ------------------------------------------------------------------------------------------
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  uint8_t* d_buf = nullptr;
+  size_t d_cap = 0;
+  uint8_t* d_aux = nullptr;   // patterns, crc parts, flags
+  size_t aux_cap = 0;
+  uint8_t* h_aux = nullptr;   // pinned mirror of small results
+  size_t h_aux_cap = 0;
+};
+
+struct DevCtx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_limit = 0;
+  GfDeviceTables* d_gf = nullptr;
+  CrcDeviceTables* d_crc[2] = {nullptr, nullptr};
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<Lane*> free_lanes;
+  int lanes_created = 0;
+  std::mutex bulk_mu;   // one multi-lane (batched) operation per device at a time
+};
+
+constexpr int kLanesPerDevice = 16;
+
+struct Global {
+  std::mutex mu;
+  bool ready = false;
+  int init_rc = CUBEEC_OK;
+  std::vector<int> devices;
+  std::vector<std::unique_ptr<DevCtx>> ctx;
+  CrcPoly poly[2] = {{0xEDB88320u}, {0x82F63B78u}};
+};
+Global g;
+
+int setup_device(DevCtx& c) {
+  CU(cudaSetDevice(c.device));
+  CU(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, c.device));
+  CU(tab_configure(&c.smem_limit));
+  GfDeviceTables gt;
+  std::memcpy(gt.log, gf().log, 256);
+  std::memcpy(gt.exp, gf().exp, 512);
+  CU(cudaMalloc(&c.d_gf, sizeof(gt)));
+  CU(cudaMemcpy(c.d_gf, &gt, sizeof(gt), cudaMemcpyHostToDevice));
+  for (int pi = 0; pi < 2; pi++) {
+    auto ct = std::make_unique<CrcDeviceTables>();
+    const CrcPoly& P = g.poly[pi];
+    crc_slice_tables(P.poly, ct->slice);
+    crc_const_mul_tables(P, P.shift_bytes_const(kTabTile), ct->shift_tile);
+    for (int t = 0; t < 1024; t++)
+      ct->kthread[t] = t < kTabThreads ? P.shift_bytes_const((int64_t)kTabTile - 16 * (t + 1)) : 0;
+    ct->poly = P.poly;
+    CU(cudaMalloc(&c.d_crc[pi], sizeof(CrcDeviceTables)));
+    CU(cudaMemcpy(c.d_crc[pi], ct.get(), sizeof(CrcDeviceTables), cudaMemcpyHostToDevice));
+  }
+  return CUBEEC_OK;
+}
+
+int ensure_init() {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (g.ready) return g.init_rc;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    t_last_error = e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA devices";
+    return CUBEEC_ERR_NO_DEVICE;   // not cached: a later call may find a device
+  }
+  if (g.devices.empty()) g.devices.push_back(0);
+  for (int d : g.devices) {
+    if (d < 0 || d >= n) return CUBEEC_ERR_INVALID_ARG;
+    auto c = std::make_unique<DevCtx>();
+    c->device = d;
+    int rc = setup_device(*c);
+    if (rc) return rc;
+    g.ctx.push_back(std::move(c));
+  }
+  g.ready = true;
+  g.init_rc = CUBEEC_OK;
+  return CUBEEC_OK;
+}
+
+DevCtx* ctx_for_device(int device) {
+  for (auto& c : g.ctx)
+    if (c->device == device) return c.get();
+  return nullptr;
+}
+
+// Borrow a lane (stream + scratch).  Blocks when all lanes of the device are in use.
+struct LaneLease {
+  DevCtx* c = nullptr;
+  Lane* lane = nullptr;
+  int acquire(DevCtx* ctx) {
+    c = ctx;
+    std::unique_lock<std::mutex> lk(c->mu);
+    for (;;) {
+      if (!c->free_lanes.empty()) {
+        lane = c->free_lanes.back();
+        c->free_lanes.pop_back();
+        break;
+      }
+      if (c->lanes_created < kLanesPerDevice) {
+        c->lanes_created++;
+        lk.unlock();
+        lane = new Lane();
+        cudaSetDevice(c->device);
+        cudaError_t e = cudaStreamCreateWithFlags(&lane->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+        break;
+      }
+      c->cv.wait(lk);
+    }
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return CUBEEC_OK;
+  }
+  ~LaneLease() {
+    if (c && lane) {
+      std::lock_guard<std::mutex> lk(c->mu);
+      c->free_lanes.push_back(lane);
+      c->cv.notify_one();
+    }
+  }
+};
+
+int lane_reserve(Lane& l, size_t d_bytes, size_t aux_bytes) {
+  if (d_bytes > l.d_cap) {
+    CU(cudaStreamSynchronize(l.stream));
+    if (l.d_buf) CU(cudaFree(l.d_buf));
+    l.d_buf = nullptr;
+    l.d_cap = 0;
+    size_t cap = round_up(d_bytes + d_bytes / 4, 1 << 20);
+    CU(cudaMalloc(&l.d_buf, cap));
+    l.d_cap = cap;
+  }
+  if (aux_bytes > l.aux_cap) {
+    CU(cudaStreamSynchronize(l.stream));
+    if (l.d_aux) CU(cudaFree(l.d_aux));
+    if (l.h_aux) CU(cudaFreeHost(l.h_aux));
+    l.d_aux = nullptr;
+    l.h_aux = nullptr;
+    size_t cap = round_up(aux_bytes * 2, 1 << 16);
+    CU(cudaMalloc(&l.d_aux, cap));
+    CU(cudaMallocHost(&l.h_aux, cap));
+    l.aux_cap = l.h_aux_cap = cap;
+  }
+  return CUBEEC_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct cubeec {
+  int k = 0, m = 0;
+  std::vector<uint8_t> gen;   // (k+m) x k
+  // encode passes: each <= kMaxOut outputs
+  std::vector<Pattern> enc_passes;
+  std::vector<Pattern> verify_passes;
+  std::vector<Pattern*> d_enc;      // per ctx: device copy [n_passes]
+  std::vector<Pattern*> d_verify;   // same, crc_in = 0
+  std::mutex mu;
+  // decode pattern cache: presence string (+data_only) -> passes
+  std::map<std::string, std::vector<Pattern>> dec_cache;
+};
+
+namespace {
+
+// Pattern passes for an arbitrary (inputs, outputs, rows) job.
+void make_passes(const std::vector<int>& in_slots, const std::vector<int>& out_slots,
+                 const std::vector<uint8_t>& rows /* n_out x n_in */, bool crc_in_first, std::vector<Pattern>& out) {
+  const int n_in = (int)in_slots.size(), n_out = (int)out_slots.size();
+  out.clear();
+  for (int o0 = 0; o0 < n_out || (o0 == 0 && crc_in_first); o0 += kMaxOut) {
+    Pattern p;
+    std::memset(&p, 0, sizeof(p));
+    p.n_in = (uint8_t)n_in;
+    p.n_out = (uint8_t)std::min(kMaxOut, n_out - o0);
+    p.crc_in = (o0 == 0 && crc_in_first) ? 1 : 0;
+    for (int c = 0; c < n_in; c++) p.in_slot[c] = (uint8_t)in_slots[c];
+    for (int r = 0; r < p.n_out; r++) {
+      p.out_slot[r] = (uint8_t)out_slots[o0 + r];
+      for (int c = 0; c < n_in; c++) p.coef[r][c] = rows[(size_t)(o0 + r) * n_in + c];
+    }
+    out.push_back(p);
+    if (n_out == 0) break;
+  }
+}
+
+// Presence pattern -> fused decode passes: every missing shard expressed directly over the
+// first k present shards (data rows from the inverse, RS/reedsolomon.go:1469-1524; parity rows
+// pre-multiplied: parity_row * decode, same values as the reference's second pass :1531-1550).
+int decode_passes(cubeec* h, const uint8_t* present, bool data_only, std::vector<Pattern>& passes) {
+  const int k = h->k, n = h->k + h->m;
+  std::string key((const char*)present, (size_t)n);
+  for (auto& ch : key) ch = ch ? 1 : 0;
+  key.push_back(data_only ? 1 : 0);
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    auto it = h->dec_cache.find(key);
+    if (it != h->dec_cache.end()) { passes = it->second; return CUBEEC_OK; }
+  }
+  std::vector<int> valid;
+  for (int i = 0; i < n && (int)valid.size() < k; i++)
+    if (present[i]) valid.push_back(i);
+  if ((int)valid.size() < k) return CUBEEC_ERR_TOO_FEW_SHARDS;
+  std::vector<uint8_t> sub((size_t)k * k), dec((size_t)k * k);
+  for (int r = 0; r < k; r++) std::memcpy(&sub[(size_t)r * k], &h->gen[(size_t)valid[r] * k], (size_t)k);
+  if (!gf_invert(sub.data(), k, dec.data())) return CUBEEC_ERR_SINGULAR;
+  std::vector<int> outs;
+  std::vector<uint8_t> rows;
+  const Gf256& G = gf();
+  for (int i = 0; i < n; i++) {
+    if (present[i]) continue;
+    if (i >= k && data_only) continue;
+    outs.push_back(i);
+    if (i < k) {
+      rows.insert(rows.end(), dec.begin() + (size_t)i * k, dec.begin() + (size_t)(i + 1) * k);
+    } else {
+      for (int c = 0; c < k; c++) {
+        uint8_t v = 0;
+        for (int j = 0; j < k; j++) v ^= G.mul(h->gen[(size_t)i * k + j], dec[(size_t)j * k + c]);
+        rows.push_back(v);
+      }
+    }
+  }
+  make_passes(valid, outs, rows, false, passes);
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->dec_cache.size() > 8192) h->dec_cache.clear();
+  h->dec_cache[key] = passes;
+  return CUBEEC_OK;
+}
+
+struct Geometry {
+  uint32_t n_seg, tiles_per_seg, tiles_last;
+  int grid;
+};
+
+Geometry pick_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes, bool per_stripe_patterns) {
+  Geometry gm;
+  const uint64_t tiles_total = (shard_len + kTabTile - 1) / kTabTile;
+  uint64_t want_items = (uint64_t)c.sm_count * (per_stripe_patterns ? 2 : 8);
+  uint64_t n_seg = (want_items + n_stripes - 1) / std::max<size_t>(n_stripes, 1);
+  const uint64_t max_seg = std::max<uint64_t>(1, tiles_total / 4);
+  n_seg = std::max<uint64_t>(1, std::min(n_seg, max_seg));
+  uint64_t tps = (tiles_total + n_seg - 1) / n_seg;
+  n_seg = (tiles_total + tps - 1) / tps;
+  gm.n_seg = (uint32_t)n_seg;
+  gm.tiles_per_seg = (uint32_t)tps;
+  gm.tiles_last = (uint32_t)(tiles_total - (n_seg - 1) * tps);
+  uint64_t items = n_stripes * n_seg;
+  gm.grid = (int)std::min<uint64_t>(items, (uint64_t)c.sm_count);
+  if (gm.grid < 1) gm.grid = 1;
+  return gm;
+}
+
+// Run `n_pass` pattern passes over a device-resident batch.  d_pass_patterns[j] points at the
+// pattern array of pass j (indexed by pattern_of_stripe, or a single pattern when that is null).
+int run_passes(DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t shard_len, size_t shard_pitch,
+               size_t stripe_pitch, size_t n_stripes, int n_slots, const std::vector<const Pattern*>& d_pass_patterns,
+               const std::vector<int>& pass_n_in, const std::vector<int>& pass_crc_slots,
+               const uint32_t* d_pattern_of_stripe, int mode, int32_t* d_mismatch, uint32_t* d_crc_part,
+               int crc_poly, const Geometry& gm) {
+  for (size_t j = 0; j < d_pass_patterns.size(); j++) {
+    TabParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.base = d_base;
+    p.stripe_pitch = stripe_pitch;
+    p.shard_pitch = shard_pitch;
+    p.shard_len = (uint32_t)shard_len;
+    p.n_stripes = (uint32_t)n_stripes;
+    p.n_seg = gm.n_seg;
+    p.tiles_per_seg = gm.tiles_per_seg;
+    p.tiles_last = gm.tiles_last;
+    p.n_slots = (uint32_t)n_slots;
+    p.patterns = d_pass_patterns[j];
+    p.pattern_of_stripe = d_pattern_of_stripe;
+    p.mode = mode;
+    p.mismatch = d_mismatch;
+    p.crc_part = d_crc_part;
+    p.gf = c.d_gf;
+    p.crc = c.d_crc[crc_poly ? 1 : 0];
+    const bool with_crc = d_crc_part != nullptr;
+    size_t smem = 0;
+    int R = tab_pick_replication(pass_n_in[j], with_crc, pass_crc_slots[j], c.smem_limit, &smem);
+    if (R == 0) return CUBEEC_ERR_UNSUPPORTED;
+    CU(launch_tab(p, R, with_crc, pass_crc_slots[j], smem, gm.grid, stream));
+    g_launches++;
+    t_last_kernel = with_crc ? "rs_tab_kernel<crc>" : "rs_tab_kernel";
+  }
+  return CUBEEC_OK;
+}
+
+int finalize_crc(DevCtx& c, cudaStream_t stream, const uint32_t* d_crc_part, size_t n_stripes, int n_slots,
+                 size_t shard_len, const Geometry& gm, int crc_poly, const uint8_t* d_slot_enable, uint32_t* d_out) {
+  (void)c;
+  const CrcPoly& P = g.poly[crc_poly ? 1 : 0];
+  CrcFinalizeParams f;
+  std::memset(&f, 0, sizeof(f));
+  f.crc_part = d_crc_part;
+  f.n_units = (uint32_t)(n_stripes * n_slots);
+  f.n_slots = (uint32_t)n_slots;
+  f.n_seg = gm.n_seg;
+  const int64_t seg_bytes = (int64_t)gm.tiles_per_seg * kTabTile;
+  const int64_t last_bytes = (int64_t)gm.tiles_last * kTabTile;
+  const int64_t virt = (int64_t)(gm.n_seg - 1) * seg_bytes + last_bytes;
+  f.x_full = P.shift_bytes_const(seg_bytes);
+  f.x_last = P.shift_bytes_const(last_bytes);
+  f.fix = P.shift_bytes_const(-(virt - (int64_t)shard_len));
+  f.init_term = P.mul(0xFFFFFFFFu, P.shift_bytes_const((int64_t)shard_len));
+  f.poly = P.poly;
+  f.slot_enable = d_slot_enable;
+  f.out = d_out;
+  CU(launch_crc_finalize(f, stream));
+  g_launches++;
+  return CUBEEC_OK;
+}
+
+// checkShards (RS/reedsolomon.go:1314-1327)
+int check_shards(const size_t* lens, int n, bool nilok, size_t* size_out) {
+  size_t size = 0;
+  for (int i = 0; i < n; i++)
+    if (lens[i]) { size = lens[i]; break; }
+  if (size == 0) return CUBEEC_ERR_SHARD_NO_DATA;
+  for (int i = 0; i < n; i++)
+    if (lens[i] != size && (lens[i] != 0 || !nilok)) return CUBEEC_ERR_SHARD_SIZE;
+  *size_out = size;
+  return CUBEEC_OK;
+}
+
+int upload_handle_patterns(cubeec* h) {
+  h->d_enc.assign(g.ctx.size(), nullptr);
+  h->d_verify.assign(g.ctx.size(), nullptr);
+  for (size_t ci = 0; ci < g.ctx.size(); ci++) {
+    CU(cudaSetDevice(g.ctx[ci]->device));
+    const size_t bytes = sizeof(Pattern) * h->enc_passes.size();
+    if (!bytes) continue;
+    CU(cudaMalloc(&h->d_enc[ci], bytes));
+    CU(cudaMemcpy(h->d_enc[ci], h->enc_passes.data(), bytes, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&h->d_verify[ci], bytes));
+    CU(cudaMemcpy(h->d_verify[ci], h->verify_passes.data(), bytes, cudaMemcpyHostToDevice));
+  }
+  return CUBEEC_OK;
+}
+
+size_t ctx_index(const DevCtx* c) {
+  for (size_t i = 0; i < g.ctx.size(); i++)
+    if (g.ctx[i].get() == c) return i;
+  return 0;
+}
+
+// Bytes of CRC scratch (per-segment remainders) an encode of this geometry needs.
+size_t crc_part_bytes(const DevCtx& c, size_t shard_len, size_t n_stripes, int n_slots) {
+  const Geometry gm = pick_geometry(c, shard_len, n_stripes, false);
+  return n_stripes * (size_t)n_slots * gm.n_seg * sizeof(uint32_t);
+}
+
+// Encode (mode 0) or verify (mode 1) a device-resident batch.  d_part: caller scratch of
+// crc_part_bytes() when CRCs are wanted, or nullptr to use the stream-ordered allocator.
+int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t shard_len,
+                    size_t shard_pitch, size_t stripe_pitch, size_t n_stripes, uint32_t* d_crc_out, int crc_poly,
+                    int mode, int32_t* d_mismatch, uint32_t* d_part) {
+  if (h->m == 0 && !d_crc_out) return CUBEEC_OK;
+  const int n = h->k + h->m;
+  const size_t ci = ctx_index(&c);
+  const Geometry gm = pick_geometry(c, shard_len, n_stripes, false);
+  const bool want_crc = mode == 0 && d_crc_out;
+  const auto& passes = want_crc ? h->enc_passes : h->verify_passes;
+  const Pattern* dp = want_crc ? h->d_enc[ci] : h->d_verify[ci];
+  std::vector<const Pattern*> pp;
+  std::vector<int> nin, ncrc;
+  for (size_t j = 0; j < passes.size(); j++) {
+    pp.push_back(dp + j);
+    nin.push_back(passes[j].n_in);
+    ncrc.push_back((passes[j].crc_in ? passes[j].n_in : 0) + passes[j].n_out);
+  }
+  bool own = false;
+  if (want_crc && !d_part) {
+    CU(cudaMallocAsync(&d_part, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
+    own = true;
+  }
+  int rc = run_passes(c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, n, pp, nin, ncrc, nullptr,
+                      mode, d_mismatch, want_crc ? d_part : nullptr, crc_poly, gm);
+  if (rc) return rc;
+  if (want_crc) {
+    rc = finalize_crc(c, stream, d_part, n_stripes, n, shard_len, gm, crc_poly, nullptr, d_crc_out);
+    if (rc) return rc;
+    if (own) CU(cudaFreeAsync(d_part, stream));
+  }
+  return CUBEEC_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// process-wide API
+// ------------------------------------------------------------------------------------------
+extern "C" int cubeec_init(const int* devices, int n_devices) {
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (g.ready) return CUBEEC_ERR_INVALID_ARG;
+    if (n_devices <= 0) return CUBEEC_ERR_INVALID_ARG;
+    g.devices.clear();
+    for (int i = 0; i < n_devices; i++) g.devices.push_back(devices ? devices[i] : i);
+  }
+  return ensure_init();
+}
+
+extern "C" int cubeec_device_count(void) {
+  int rc = ensure_init();
+  if (rc) return 0;
+  return (int)g.ctx.size();
+}
+
+extern "C" int cubeec_host_alloc(size_t bytes, void** out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  CU(cudaMallocHost(out, bytes));
+  return CUBEEC_OK;
+}
+extern "C" int cubeec_host_free(void* p) {
+  CU(cudaFreeHost(p));
+  return CUBEEC_OK;
+}
+extern "C" int cubeec_host_register(void* p, size_t bytes) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return CUBEEC_OK;
+}
+extern "C" int cubeec_host_unregister(void* p) {
+  CU(cudaHostUnregister(p));
+  return CUBEEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// handle API
+// ------------------------------------------------------------------------------------------
+extern "C" int cubeec_create(int k, int m, const uint8_t* parity_rows, cubeec_t** out) {
+  if (!out) return CUBEEC_ERR_INVALID_ARG;
+  *out = nullptr;
+  // argument checks first, in the reference's order (RS/reedsolomon.go:419-441)
+  if (k + m > 256) return CUBEEC_ERR_MAX_SHARD_NUM;
+  if (k <= 0 || m < 0) return CUBEEC_ERR_INV_SHARD_NUM;
+  if (k > kMaxIn) return CUBEEC_ERR_UNSUPPORTED;
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto h = std::make_unique<cubeec>();
+  h->k = k;
+  h->m = m;
+  if (m == 0 || parity_rows) {
+    h->gen.assign((size_t)(k + m) * k, 0);
+    for (int i = 0; i < k; i++) h->gen[(size_t)i * k + i] = 1;
+    if (m) std::memcpy(&h->gen[(size_t)k * k], parity_rows, (size_t)m * k);
+  } else if (!build_generator(k, k + m, h->gen)) {
+    return CUBEEC_ERR_SINGULAR;
+  }
+  if (m > 0) {
+    std::vector<int> ins, outs;
+    for (int i = 0; i < k; i++) ins.push_back(i);
+    for (int i = 0; i < m; i++) outs.push_back(k + i);
+    std::vector<uint8_t> rows(h->gen.begin() + (size_t)k * k, h->gen.end());
+    make_passes(ins, outs, rows, true, h->enc_passes);
+    make_passes(ins, outs, rows, false, h->verify_passes);
+    rc = upload_handle_patterns(h.get());
+    if (rc) return rc;
+  }
+  *out = h.release();
+  return CUBEEC_OK;
+}
+
+extern "C" void cubeec_destroy(cubeec_t* h) {
+  if (!h) return;
+  for (size_t ci = 0; ci < h->d_enc.size() && ci < g.ctx.size(); ci++) {
+    cudaSetDevice(g.ctx[ci]->device);
+    if (h->d_enc[ci]) cudaFree(h->d_enc[ci]);
+    if (h->d_verify[ci]) cudaFree(h->d_verify[ci]);
+  }
+  delete h;
+}
+extern "C" int cubeec_k(const cubeec_t* h) { return h ? h->k : 0; }
+extern "C" int cubeec_m(const cubeec_t* h) { return h ? h->m : 0; }
+extern "C" int cubeec_matrix(const cubeec_t* h, uint8_t* out) {
+  if (!h || !out) return CUBEEC_ERR_INVALID_ARG;
+  std::memcpy(out, h->gen.data(), h->gen.size());
+  return CUBEEC_OK;
+}
+extern "C" int cubeec_decode_matrix(const cubeec_t* h, const uint8_t* present, int* valid, uint8_t* rows) {
+  if (!h || !present || !valid || !rows) return CUBEEC_ERR_INVALID_ARG;
+  const int k = h->k, n = h->k + h->m;
+  int cnt = 0;
+  for (int i = 0; i < n && cnt < k; i++)
+    if (present[i]) valid[cnt++] = i;
+  if (cnt < k) return CUBEEC_ERR_TOO_FEW_SHARDS;
+  std::vector<uint8_t> sub((size_t)k * k);
+  for (int r = 0; r < k; r++) std::memcpy(&sub[(size_t)r * k], &h->gen[(size_t)valid[r] * k], (size_t)k);
+  return gf_invert(sub.data(), k, rows) ? CUBEEC_OK : CUBEEC_ERR_SINGULAR;
+}
+
+// ------------------------------------------------------------------------------------------
+// device-resident API
+// ------------------------------------------------------------------------------------------
+static int check_dev_layout(const void* d_base, size_t shard_len, size_t shard_pitch, size_t stripe_pitch) {
+  if (!d_base || shard_len == 0) return CUBEEC_ERR_INVALID_ARG;
+  if (((uintptr_t)d_base & 15) || (shard_pitch & 15) || (stripe_pitch & 15) || shard_pitch < shard_len)
+    return CUBEEC_ERR_INVALID_ARG;
+  if (shard_len > 0xFFFFFFF0ull) return CUBEEC_ERR_UNSUPPORTED;
+  return CUBEEC_OK;
+}
+
+extern "C" int cubeec_dev_encode(cubeec_t* h, int device, void* d_base, size_t shard_len, size_t shard_pitch,
+                                 size_t stripe_pitch, size_t n_stripes, uint32_t* d_crc_out, int crc_poly,
+                                 void* stream) {
+  if (!h) return CUBEEC_ERR_INVALID_ARG;
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch))) return rc;
+  if (n_stripes == 0) return CUBEEC_OK;
+  DevCtx* c = ctx_for_device(device);
+  if (!c) return CUBEEC_ERR_INVALID_ARG;
+  CU(cudaSetDevice(device));
+  if (stream) {
+    return dev_encode_impl(h, *c, (cudaStream_t)stream, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch,
+                           n_stripes, d_crc_out, crc_poly, 0, nullptr, nullptr);
+  }
+  LaneLease lease;
+  if ((rc = lease.acquire(c))) return rc;
+  uint32_t* d_part = nullptr;
+  if (d_crc_out) {
+    if ((rc = lane_reserve(*lease.lane, 0, crc_part_bytes(*c, shard_len, n_stripes, h->k + h->m)))) return rc;
+    d_part = reinterpret_cast<uint32_t*>(lease.lane->d_aux);
+  }
+  rc = dev_encode_impl(h, *c, lease.lane->stream, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch, n_stripes,
+                       d_crc_out, crc_poly, 0, nullptr, d_part);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(lease.lane->stream));
+  return CUBEEC_OK;
+}
+
+extern "C" int cubeec_dev_verify(cubeec_t* h, int device, const void* d_base, size_t shard_len, size_t shard_pitch,
+                                 size_t stripe_pitch, size_t n_stripes, int32_t* d_ok, void* stream) {
+  if (!h || !d_ok) return CUBEEC_ERR_INVALID_ARG;
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch))) return rc;
+  if (n_stripes == 0) return CUBEEC_OK;
+  DevCtx* c = ctx_for_device(device);
+  if (!c) return CUBEEC_ERR_INVALID_ARG;
+  CU(cudaSetDevice(device));
+  LaneLease lease;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    if ((rc = lease.acquire(c))) return rc;
+    st = lease.lane->stream;
+  }
+  // d_ok doubles as the mismatch flag array: kernel sets 1 on mismatch, then it is inverted.
+  CU(cudaMemsetAsync(d_ok, 0, n_stripes * sizeof(int32_t), st));
+  rc = dev_encode_impl(h, *c, st, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, nullptr, 0, 1,
+                       d_ok, nullptr);
+  if (rc) return rc;
+  CU(launch_invert_flags(d_ok, n_stripes, st));   // ok = !mismatch
+  g_launches++;
+  if (!stream) CU(cudaStreamSynchronize(st));
+  return CUBEEC_OK;
+}
+
+extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, size_t shard_len, size_t shard_pitch,
+                                      size_t stripe_pitch, size_t n_stripes, const uint8_t* present, int data_only,
+                                      void* stream) {
+  if (!h || !present) return CUBEEC_ERR_INVALID_ARG;
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch))) return rc;
+  if (n_stripes == 0) return CUBEEC_OK;
+  DevCtx* c = ctx_for_device(device);
+  if (!c) return CUBEEC_ERR_INVALID_ARG;
+  CU(cudaSetDevice(device));
+  const int n = h->k + h->m;
+  // distinct presence patterns -> pattern ids
+  std::map<std::string, uint32_t> ids;
+  std::vector<std::vector<Pattern>> pat_passes;
+  std::vector<uint32_t> pos(n_stripes);
+  size_t n_pass = 0;
+  for (size_t s = 0; s < n_stripes; s++) {
+    std::string key((const char*)present + s * n, (size_t)n);
+    for (auto& ch : key) ch = ch ? 1 : 0;
+    auto it = ids.find(key);
+    if (it == ids.end()) {
+      std::vector<Pattern> passes;
+      rc = decode_passes(h, (const uint8_t*)key.data(), data_only != 0, passes);
+      if (rc) return rc;
+      n_pass = std::max(n_pass, passes.size());
+      it = ids.emplace(key, (uint32_t)pat_passes.size()).first;
+      pat_passes.push_back(std::move(passes));
+    }
+    pos[s] = it->second;
+  }
+  // drop passes that do nothing for every pattern
+  while (n_pass > 0) {
+    bool any = false;
+    for (auto& pp : pat_passes)
+      if (pp.size() >= n_pass && pp[n_pass - 1].n_out) any = true;
+    if (any) break;
+    n_pass--;
+  }
+  if (n_pass == 0) return CUBEEC_OK;
+  const size_t n_pat = pat_passes.size();
+  std::vector<Pattern> flat(n_pass * n_pat);
+  std::memset(flat.data(), 0, flat.size() * sizeof(Pattern));
+  std::vector<int> nin(n_pass, 0), ncrc(n_pass, 0);
+  for (size_t j = 0; j < n_pass; j++)
+    for (size_t q = 0; q < n_pat; q++)
+      if (j < pat_passes[q].size()) {
+        flat[j * n_pat + q] = pat_passes[q][j];
+        nin[j] = std::max<int>(nin[j], pat_passes[q][j].n_in);
+      }
+  LaneLease lease;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    if ((rc = lease.acquire(c))) return rc;
+    st = lease.lane->stream;
+  }
+  Pattern* d_pat = nullptr;
+  uint32_t* d_pos = nullptr;
+  CU(cudaMallocAsync(&d_pat, flat.size() * sizeof(Pattern), st));
+  CU(cudaMallocAsync(&d_pos, n_stripes * sizeof(uint32_t), st));
+  CU(cudaMemcpyAsync(d_pat, flat.data(), flat.size() * sizeof(Pattern), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_pos, pos.data(), n_stripes * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  std::vector<const Pattern*> pp;
+  for (size_t j = 0; j < n_pass; j++) pp.push_back(d_pat + j * n_pat);
+  const Geometry gm = pick_geometry(*c, shard_len, n_stripes, n_pat > 1);
+  rc = run_passes(*c, st, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, n, pp, nin, ncrc, d_pos,
+                  0, nullptr, nullptr, 0, gm);
+  if (rc) return rc;
+  CU(cudaFreeAsync(d_pat, st));
+  CU(cudaFreeAsync(d_pos, st));
+  // the host staging vectors (flat, pos) are pageable: the async copies above were staged by the
+  // runtime before returning, so they may go out of scope here.
+  if (!stream) CU(cudaStreamSynchronize(st));
+  return CUBEEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// single stripe, host scatter pointers
+// ------------------------------------------------------------------------------------------
+extern "C" int cubeec_encode(cubeec_t* h, uint8_t* const* shards, const size_t* lens, int n, uint32_t* crc_out,
+                             int crc_poly) {
+  if (!h || !shards || !lens) return CUBEEC_ERR_INVALID_ARG;
+  if (n != h->k + h->m) return CUBEEC_ERR_TOO_FEW_SHARDS;
+  size_t S = 0;
+  int rc = check_shards(lens, n, false, &S);
+  if (rc) return rc;
+  if ((rc = ensure_init())) return rc;
+  DevCtx* c = g.ctx[0].get();
+  LaneLease lease;
+  if ((rc = lease.acquire(c))) return rc;
+  Lane& l = *lease.lane;
+  const size_t P = round_up(S, kAlign);
+  const size_t part_bytes = round_up(crc_part_bytes(*c, S, 1, n), 256);
+  if ((rc = lane_reserve(l, P * n, part_bytes + (size_t)n * 4 + 256))) return rc;
+  for (int i = 0; i < h->k; i++) CU(cudaMemcpyAsync(l.d_buf + i * P, shards[i], S, cudaMemcpyHostToDevice, l.stream));
+  uint32_t* d_part = reinterpret_cast<uint32_t*>(l.d_aux);
+  uint32_t* d_crc = crc_out ? reinterpret_cast<uint32_t*>(l.d_aux + part_bytes) : nullptr;
+  rc = dev_encode_impl(h, *c, l.stream, l.d_buf, S, P, P * n, 1, d_crc, crc_poly, 0, nullptr, d_part);
+  if (rc) return rc;
+  for (int i = h->k; i < n; i++) CU(cudaMemcpyAsync(shards[i], l.d_buf + i * P, S, cudaMemcpyDeviceToHost, l.stream));
+  if (crc_out) CU(cudaMemcpyAsync(crc_out, d_crc, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
+  CU(cudaStreamSynchronize(l.stream));
+  return CUBEEC_OK;
+}
+
+extern "C" int cubeec_verify(cubeec_t* h, uint8_t* const* shards, const size_t* lens, int n, int* ok) {
+  if (!h || !shards || !lens || !ok) return CUBEEC_ERR_INVALID_ARG;
+  *ok = 0;
+  if (n != h->k + h->m) return CUBEEC_ERR_TOO_FEW_SHARDS;
+  size_t S = 0;
+  int rc = check_shards(lens, n, false, &S);
+  if (rc) return rc;
+  if (h->m == 0) { *ok = 1; return CUBEEC_OK; }
+  if ((rc = ensure_init())) return rc;
+  DevCtx* c = g.ctx[0].get();
+  LaneLease lease;
+  if ((rc = lease.acquire(c))) return rc;
+  Lane& l = *lease.lane;
+  const size_t P = round_up(S, kAlign);
+  if ((rc = lane_reserve(l, P * n, 4096))) return rc;
+  for (int i = 0; i < n; i++) CU(cudaMemcpyAsync(l.d_buf + i * P, shards[i], S, cudaMemcpyHostToDevice, l.stream));
+  int32_t* d_flag = reinterpret_cast<int32_t*>(l.d_aux);
+  CU(cudaMemsetAsync(d_flag, 0, sizeof(int32_t), l.stream));
+  rc = dev_encode_impl(h, *c, l.stream, l.d_buf, S, P, P * n, 1, nullptr, 0, 1, d_flag, nullptr);
+  if (rc) return rc;
+  int32_t flag = 1;
+  CU(cudaMemcpyAsync(&flag, d_flag, sizeof(flag), cudaMemcpyDeviceToHost, l.stream));
+  CU(cudaStreamSynchronize(l.stream));
+  *ok = flag ? 0 : 1;
+  return CUBEEC_OK;
+}
+
+namespace {
+// Shared by cubeec_reconstruct and the batch variant: issues all work for one stripe on a lane.
+// Does not synchronize unless crc_out is given.  Small host->device control data (patterns,
+// enable flags) is copied from pageable memory, which the runtime stages before returning, so a
+// lane can be reused for the next stripe without a host-side wait.
+int reconstruct_issue(cubeec* h, DevCtx& c, Lane& l, uint8_t* const* shards, const uint8_t* present, size_t S,
+                      bool data_only, uint8_t* filled, uint32_t* crc_out, int crc_poly, bool* did_work,
+                      int32_t* verify_flag_host) {
+  const int k = h->k, n = h->k + h->m;
+  *did_work = false;
+  int number_present = 0, data_present = 0;
+  for (int i = 0; i < n; i++)
+    if (present[i]) { number_present++; if (i < k) data_present++; }
+  // RS/reedsolomon.go:1434-1444: nothing to do / too few
+  const bool nothing = number_present == n || (data_only && data_present == k);
+  if (nothing && !verify_flag_host) return CUBEEC_OK;
+  if (!nothing && number_present < k) return CUBEEC_ERR_TOO_FEW_SHARDS;
+  std::vector<Pattern> passes;
+  if (!nothing) {
+    int rc = decode_passes(h, present, data_only, passes);
+    if (rc) return rc;
+  }
+  const size_t P = round_up(S, kAlign);
+  const Geometry gm = pick_geometry(c, S, 1, false);
+  // aux layout
+  const size_t o_pat = 0;
+  const size_t o_flag = o_pat + round_up(sizeof(Pattern) * std::max<size_t>(passes.size(), 1), 256);
+  const size_t o_crc = o_flag + 256;
+  const size_t o_en = o_crc + round_up((size_t)n * 4, 256);
+  const size_t o_part = o_en + round_up((size_t)n, 256);
+  const size_t aux_total = o_part + round_up((size_t)n * gm.n_seg * 4, 256);
+  int rc = lane_reserve(l, P * n, aux_total);
+  if (rc) return rc;
+  // which shards have to travel: the k survivors used as inputs (all present ones when verifying)
+  std::vector<uint8_t> need(n, 0);
+  if (verify_flag_host) {
+    for (int i = 0; i < n; i++) need[i] = present[i];
+  } else if (!passes.empty()) {
+    for (int c2 = 0; c2 < passes[0].n_in; c2++) need[passes[0].in_slot[c2]] = 1;
+  }
+  for (int i = 0; i < n; i++)
+    if (need[i]) CU(cudaMemcpyAsync(l.d_buf + i * P, shards[i], S, cudaMemcpyHostToDevice, l.stream));
+  Pattern* d_pat = reinterpret_cast<Pattern*>(l.d_aux + o_pat);
+  int32_t* d_flag = reinterpret_cast<int32_t*>(l.d_aux + o_flag);
+  uint32_t* d_crc = reinterpret_cast<uint32_t*>(l.d_aux + o_crc);
+  uint8_t* d_enable = l.d_aux + o_en;
+  uint32_t* d_part = crc_out ? reinterpret_cast<uint32_t*>(l.d_aux + o_part) : nullptr;
+  if (!passes.empty()) {
+    CU(cudaMemcpyAsync(d_pat, passes.data(), sizeof(Pattern) * passes.size(), cudaMemcpyHostToDevice, l.stream));
+    std::vector<const Pattern*> pp;
+    std::vector<int> nin, ncrc;
+    for (size_t j = 0; j < passes.size(); j++) {
+      pp.push_back(d_pat + j);
+      nin.push_back(passes[j].n_in);
+      ncrc.push_back(passes[j].n_out);
+    }
+    rc = run_passes(c, l.stream, l.d_buf, S, P, P * n, 1, n, pp, nin, ncrc, nullptr, 0, nullptr, d_part, crc_poly, gm);
+    if (rc) return rc;
+    std::vector<uint8_t> enable(n, 0);
+    for (auto& ps : passes)
+      for (int r = 0; r < ps.n_out; r++) {
+        const int slot = ps.out_slot[r];
+        enable[slot] = 1;
+        if (filled) filled[slot] = 1;
+        CU(cudaMemcpyAsync(shards[slot], l.d_buf + slot * P, S, cudaMemcpyDeviceToHost, l.stream));
+      }
+    if (crc_out) {
+      CU(cudaMemcpyAsync(d_enable, enable.data(), (size_t)n, cudaMemcpyHostToDevice, l.stream));
+      rc = finalize_crc(c, l.stream, d_part, 1, n, S, gm, crc_poly, d_enable, d_crc);
+      if (rc) return rc;
+      std::vector<uint32_t> h_crc(n);
+      CU(cudaMemcpyAsync(h_crc.data(), d_crc, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
+      CU(cudaStreamSynchronize(l.stream));
+      for (int i = 0; i < n; i++)
+        if (enable[i]) crc_out[i] = h_crc[i];
+    }
+    *did_work = true;
+  }
+  if (verify_flag_host) {
+    // the repair loop's Verify right after Reconstruct (worker_slice_recover.go:871)
+    CU(cudaMemsetAsync(d_flag, 0, sizeof(int32_t), l.stream));
+    rc = dev_encode_impl(h, c, l.stream, l.d_buf, S, P, P * n, 1, nullptr, 0, 1, d_flag, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(verify_flag_host, d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, l.stream));
+    *did_work = true;
+  }
+  return CUBEEC_OK;
+}
+}  // namespace
+
+extern "C" int cubeec_reconstruct(cubeec_t* h, uint8_t* const* shards, const size_t* lens, int n, int data_only,
+                                  uint8_t* filled, uint32_t* crc_out, int crc_poly) {
+  if (!h || !shards || !lens) return CUBEEC_ERR_INVALID_ARG;
+  if (filled && n > 0) std::memset(filled, 0, (size_t)n);
+  if (n != h->k + h->m) return CUBEEC_ERR_TOO_FEW_SHARDS;
+  size_t S = 0;
+  int rc = check_shards(lens, n, true, &S);
+  if (rc) return rc;
+  std::vector<uint8_t> present(n);
+  for (int i = 0; i < n; i++) present[i] = lens[i] != 0;
+  if ((rc = ensure_init())) return rc;
+  DevCtx* c = g.ctx[0].get();
+  LaneLease lease;
+  if ((rc = lease.acquire(c))) return rc;
+  bool did = false;
+  rc = reconstruct_issue(h, *c, *lease.lane, shards, present.data(), S, data_only != 0, filled, crc_out, crc_poly, &did,
+                         nullptr);
+  if (rc) return rc;
+  if (did) CU(cudaStreamSynchronize(lease.lane->stream));
+  return CUBEEC_OK;
+}
+
+extern "C" int cubeec_reconstruct_batch(cubeec_t* h, const cubeec_stripe_t* stripes, size_t n_stripes, int data_only,
+                                        int* verify_ok) {
+  if (!h || (!stripes && n_stripes)) return CUBEEC_ERR_INVALID_ARG;
+  int rc = ensure_init();
+  if (rc) return rc;
+  const int n = h->k + h->m;
+  // Stripes are dealt round-robin to (device, lane) pairs; stream order keeps each lane's
+  // staging buffer safe for reuse, so the host never waits between stripes.
+  const size_t n_ctx = g.ctx.size();
+  std::vector<std::unique_ptr<std::lock_guard<std::mutex>>> bulk;
+  for (size_t ci = 0; ci < n_ctx; ci++) bulk.push_back(std::make_unique<std::lock_guard<std::mutex>>(g.ctx[ci]->bulk_mu));
+  std::vector<std::unique_ptr<LaneLease>> leases;
+  for (size_t ci = 0; ci < n_ctx; ci++)
+    for (int q = 0; q < 2; q++) {
+      auto ls = std::make_unique<LaneLease>();
+      if ((rc = ls->acquire(g.ctx[ci].get()))) return rc;
+      leases.push_back(std::move(ls));
+    }
+  std::vector<int32_t*> flags(leases.size(), nullptr);
+  int32_t* h_flags = nullptr;
+  if (verify_ok) {
+    CU(cudaMallocHost(&h_flags, sizeof(int32_t) * std::max<size_t>(n_stripes, 1)));
+    for (size_t s = 0; s < n_stripes; s++) h_flags[s] = 0;
+  }
+  int result = CUBEEC_OK;
+  for (size_t s = 0; s < n_stripes && result == CUBEEC_OK; s++) {
+    LaneLease& ls = *leases[s % leases.size()];
+    cudaSetDevice(ls.c->device);
+    const cubeec_stripe_t& sp = stripes[s];
+    if (!sp.shards || !sp.present || sp.shard_len == 0) { result = CUBEEC_ERR_INVALID_ARG; break; }
+    bool did = false;
+    (void)n;
+    result = reconstruct_issue(h, *ls.c, *ls.lane, sp.shards, sp.present, sp.shard_len, data_only != 0, nullptr, nullptr,
+                               0, &did, verify_ok ? &h_flags[s] : nullptr);
+  }
+  for (auto& ls : leases) {
+    cudaSetDevice(ls->c->device);
+    cudaError_t e = cudaStreamSynchronize(ls->lane->stream);
+    if (e != cudaSuccess && result == CUBEEC_OK) result = cuda_fail(e, "cudaStreamSynchronize");
+  }
+  if (verify_ok) {
+    for (size_t s = 0; s < n_stripes; s++) verify_ok[s] = h_flags[s] ? 0 : 1;
+    cudaFreeHost(h_flags);
+  }
+  return result;
+}
+
+// ------------------------------------------------------------------------------------------
+// batched host-contiguous encode (ec.Buffer layout), pipelined H2D / kernel / D2H over lanes
+// and partitioned over the configured devices.
+// ------------------------------------------------------------------------------------------
+namespace {
+int encode_contig_device(cubeec* h, DevCtx* c, uint8_t* base, size_t S, size_t first, size_t count, size_t stripe_pitch,
+                         uint32_t* crc_out, int crc_poly) {
+  const int k = h->k, n = h->k + h->m, m = h->m;
+  const size_t P = round_up(S, kAlign);
+  const size_t dstripe = P * n;
+  std::lock_guard<std::mutex> bulk(c->bulk_mu);
+  // chunk: up to ~256 MiB of device staging per lane
+  size_t chunk = std::max<size_t>(1, (256u << 20) / dstripe);
+  chunk = std::min(chunk, count);
+  const int n_lanes = 3;
+  // CRC scratch bound for any chunk of <= `chunk` stripes: nb * n_seg(nb) <= 8*SMs + nb
+  const size_t part_cap = round_up((size_t)n * (8 * (size_t)c->sm_count + chunk + 8) * 4, 256);
+  const size_t crc_cap = round_up(chunk * n * 4, 256);
+  std::vector<std::unique_ptr<LaneLease>> leases;
+  for (int q = 0; q < n_lanes; q++) {
+    auto ls = std::make_unique<LaneLease>();
+    int rc = ls->acquire(c);
+    if (rc) return rc;
+    rc = lane_reserve(*ls->lane, dstripe * chunk, crc_out ? part_cap + crc_cap : 256);
+    if (rc) return rc;
+    leases.push_back(std::move(ls));
+  }
+  size_t done = 0, ci = 0;
+  while (done < count) {
+    const size_t nb = std::min(chunk, count - done);
+    Lane& l = *leases[ci % n_lanes]->lane;
+    for (size_t s = 0; s < nb; s++) {
+      const uint8_t* src = base + (first + done + s) * stripe_pitch;
+      CU(cudaMemcpy2DAsync(l.d_buf + s * dstripe, P, src, S, S, (size_t)k, cudaMemcpyHostToDevice, l.stream));
+    }
+    uint32_t* d_part = crc_out ? reinterpret_cast<uint32_t*>(l.d_aux) : nullptr;
+    uint32_t* d_crc = crc_out ? reinterpret_cast<uint32_t*>(l.d_aux + part_cap) : nullptr;
+    if (crc_out && crc_part_bytes(*c, S, nb, n) > part_cap) return CUBEEC_ERR_UNSUPPORTED;
+    int rc = dev_encode_impl(h, *c, l.stream, l.d_buf, S, P, dstripe, nb, d_crc, crc_poly, 0, nullptr, d_part);
+    if (rc) return rc;
+    if (crc_out)
+      CU(cudaMemcpyAsync(crc_out + (first + done) * n, d_crc, nb * n * 4, cudaMemcpyDeviceToHost, l.stream));
+    for (size_t s = 0; s < nb && m > 0; s++) {
+      uint8_t* dst = base + (first + done + s) * stripe_pitch + (size_t)k * S;
+      CU(cudaMemcpy2DAsync(dst, S, l.d_buf + s * dstripe + (size_t)k * P, P, S, (size_t)m, cudaMemcpyDeviceToHost,
+                           l.stream));
+    }
+    done += nb;
+    ci++;
+  }
+  for (auto& ls : leases) CU(cudaStreamSynchronize(ls->lane->stream));
+  return CUBEEC_OK;
+}
+}  // namespace
+
+extern "C" int cubeec_encode_contig(cubeec_t* h, uint8_t* base, size_t shard_len, size_t n_stripes, size_t stripe_pitch,
+                                    uint32_t* crc_out, uint32_t* blockcrc_out, size_t block_payload, int crc_poly) {
+  if (!h || !base || shard_len == 0) return CUBEEC_ERR_INVALID_ARG;
+  if (stripe_pitch < shard_len * (size_t)(h->k + h->m)) return CUBEEC_ERR_INVALID_ARG;
+  if (blockcrc_out && block_payload == 0) return CUBEEC_ERR_INVALID_ARG;
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (n_stripes == 0) return CUBEEC_OK;
+  if (h->m == 0 && !crc_out && !blockcrc_out) return CUBEEC_OK;
+  const size_t n_ctx = g.ctx.size();
+  std::vector<int> rcs(n_ctx, CUBEEC_OK);
+  std::vector<std::string> errs(n_ctx);
+  auto work = [&](size_t ci) {
+    const size_t first = n_stripes * ci / n_ctx, last = n_stripes * (ci + 1) / n_ctx;
+    if (last > first) {
+      cudaSetDevice(g.ctx[ci]->device);
+      rcs[ci] = encode_contig_device(h, g.ctx[ci].get(), base, shard_len, first, last - first, stripe_pitch, crc_out,
+                                     crc_poly);
+      if (rcs[ci]) errs[ci] = t_last_error;
+    }
+  };
+  if (n_ctx == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t ci = 0; ci < n_ctx; ci++) th.emplace_back(work, ci);
+    for (auto& t : th) t.join();
+  }
+  for (size_t ci = 0; ci < n_ctx; ci++)
+    if (rcs[ci]) { t_last_error = errs[ci]; return rcs[ci]; }
+  if (blockcrc_out) {
+    // per-block CRCs of every shard (crc32block framing order): one flat pass per stripe row set
+    const int n = h->k + h->m;
+    const size_t units = (shard_len + block_payload - 1) / block_payload;
+    for (size_t s = 0; s < n_stripes; s++)
+      for (int i = 0; i < n; i++) {
+        rc = cubeec_crc32_blocks(base + s * stripe_pitch + (size_t)i * shard_len, shard_len, block_payload, crc_poly,
+                                 blockcrc_out + (s * n + i) * units, nullptr);
+        if (rc) return rc;
+      }
+  }
+  return CUBEEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// CRC32 surface
+// ------------------------------------------------------------------------------------------
+namespace {
+int dev_crc32_impl(DevCtx& c, cudaStream_t st, const uint8_t* d_base, size_t len, size_t pitch, size_t n_buffers,
+                   size_t block, int crc_poly, uint32_t* d_whole, uint32_t* d_blocks) {
+  // internal unit: the caller's block, or 64 KiB slices when only the whole CRC is wanted
+  const size_t unit = block ? block : std::min<size_t>(len, 1u << 16);
+  const size_t units = (len + unit - 1) / unit;
+  uint32_t* d_units = d_blocks;
+  bool own = false;
+  if (!d_units || !block) {
+    CU(cudaMallocAsync(&d_units, n_buffers * units * 4, st));
+    own = true;
+  }
+  CrcRangeParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.base = d_base;
+  p.pitch = pitch;
+  p.n_buffers = (uint32_t)n_buffers;
+  p.len = (uint32_t)len;
+  p.block = (uint32_t)unit;
+  p.units_per_buffer = (uint32_t)units;
+  p.crc = c.d_crc[crc_poly ? 1 : 0];
+  p.out = d_units;
+  const uint64_t total = (uint64_t)n_buffers * units;
+  const int grid = (int)std::min<uint64_t>(total, (uint64_t)c.sm_count * 4);
+  CU(launch_crc_ranges(p, grid, st));
+  g_launches++;
+  t_last_kernel = "crc_range_kernel";
+  if (d_whole) {
+    CU(launch_crc_combine(d_units, (uint32_t)n_buffers, (uint32_t)units, (uint32_t)len, (uint32_t)unit,
+                          g.poly[crc_poly ? 1 : 0].poly, d_whole, st));
+    g_launches++;
+  }
+  if (own) CU(cudaFreeAsync(d_units, st));
+  return CUBEEC_OK;
+}
+}  // namespace
+
+extern "C" int cubeec_dev_crc32(int device, const void* d_base, size_t len, size_t pitch, size_t n_buffers,
+                                size_t block_payload, int crc_poly, uint32_t* d_whole, uint32_t* d_blocks,
+                                void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!d_base || len == 0 || ((uintptr_t)d_base & 15) || (pitch & 15) || len > 0xFFFFFFF0ull)
+    return CUBEEC_ERR_INVALID_ARG;
+  if (n_buffers == 0) return CUBEEC_OK;
+  DevCtx* c = ctx_for_device(device);
+  if (!c) return CUBEEC_ERR_INVALID_ARG;
+  CU(cudaSetDevice(device));
+  LaneLease lease;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    if ((rc = lease.acquire(c))) return rc;
+    st = lease.lane->stream;
+  }
+  rc = dev_crc32_impl(*c, st, (const uint8_t*)d_base, len, pitch, n_buffers, block_payload, crc_poly, d_whole, d_blocks);
+  if (rc) return rc;
+  if (!stream) CU(cudaStreamSynchronize(st));
+  return CUBEEC_OK;
+}
+
+extern "C" int cubeec_crc32_blocks(const uint8_t* p, size_t n, size_t block_payload, int crc_poly, uint32_t* per_block,
+                                   uint32_t* whole) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (n == 0) {
+    if (whole) *whole = 0;   // crc32 of the empty string
+    return CUBEEC_OK;
+  }
+  if (!p || n > 0xFFFFFFF0ull) return CUBEEC_ERR_INVALID_ARG;
+  DevCtx* c = g.ctx[0].get();
+  LaneLease lease;
+  if ((rc = lease.acquire(c))) return rc;
+  Lane& l = *lease.lane;
+  const size_t units = block_payload ? (n + block_payload - 1) / block_payload : 0;
+  const size_t aux = round_up(units * 4, 256) + 512;
+  if ((rc = lane_reserve(l, round_up(n, kAlign), aux))) return rc;
+  CU(cudaMemcpyAsync(l.d_buf, p, n, cudaMemcpyHostToDevice, l.stream));
+  uint32_t* d_blocks = units ? reinterpret_cast<uint32_t*>(l.d_aux) : nullptr;
+  uint32_t* d_whole = reinterpret_cast<uint32_t*>(l.d_aux + round_up(units * 4, 256));
+  rc = dev_crc32_impl(*c, l.stream, l.d_buf, n, round_up(n, kAlign), 1, block_payload, crc_poly, whole ? d_whole : nullptr,
+                      (per_block && units) ? d_blocks : nullptr);
+  if (rc) return rc;
+  if (per_block && units) CU(cudaMemcpyAsync(per_block, d_blocks, units * 4, cudaMemcpyDeviceToHost, l.stream));
+  if (whole) CU(cudaMemcpyAsync(whole, d_whole, 4, cudaMemcpyDeviceToHost, l.stream));
+  CU(cudaStreamSynchronize(l.stream));
+  return CUBEEC_OK;
+}
+
+extern "C" int cubeec_crc32(const uint8_t* p, size_t n, int crc_poly, uint32_t* out) {
+  if (!out) return CUBEEC_ERR_INVALID_ARG;
+  return cubeec_crc32_blocks(p, n, 0, crc_poly, nullptr, out);
+}

@@ -1,0 +1,486 @@
+// kernels.cu -- sm_100a kernels of libcubeec: generic table-driven GF(2^8) coding kernel
+// (encode / reconstruct / verify for any k, any coefficients) with an optional fused CRC32 pass,
+// plus the CRC finalize / range kernels.
+//
+// Replaces the CPU SIMD kernels of klauspost/reedsolomon (mulAvxTwo_* / mulGFNI_*,
+// RS/galois_gen_amd64.s) and Go's hash/crc32 on the BlobStore shard path.  No tensor cores:
+// this is byte-field arithmetic, bounded by HBM bandwidth, LSU (shared-memory lookups) and the
+// integer ALU pipe.  See DESIGN.md for the roofline of each kernel.
+#include "kernels.cuh"
+
+namespace cbe {
+
+// ------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+// zero the bytes at positions >= n (0 < n < 16) of a 16-byte piece
+__device__ __forceinline__ uint4 keep_head(uint4 d, int n) {
+  uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int rem = n - 4 * i;
+    if (rem <= 0) w[i] = 0;
+    else if (rem < 4) w[i] &= (1u << (8 * rem)) - 1u;
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+// zero the bytes at positions < n (0 < n < 16)
+__device__ __forceinline__ uint4 drop_head(uint4 d, int n) {
+  uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int rem = n - 4 * i;
+    if (rem >= 4) w[i] = 0;
+    else if (rem > 0) w[i] &= ~((1u << (8 * rem)) - 1u);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// a(x)*b(x) mod P in the reflected representation (bit 31 = x^0)
+__device__ __forceinline__ uint32_t gf32_mul(uint32_t a, uint32_t b, uint32_t poly) {
+  uint32_t r = 0;
+#pragma unroll 8
+  for (int i = 0; i < 32; i++) {
+    r ^= a & (uint32_t)((int32_t)b >> 31);
+    b <<= 1;
+    a = (a >> 1) ^ (poly & (0u - (a & 1u)));
+  }
+  return r;
+}
+// x^n mod P for n >= 0
+__device__ uint32_t gf32_xpow(uint64_t n, uint32_t poly) {
+  uint32_t result = 0x80000000u, base = 0x40000000u;
+  while (n) {
+    if (n & 1) result = gf32_mul(result, base, poly);
+    base = gf32_mul(base, base, poly);
+    n >>= 1;
+  }
+  return result;
+}
+
+// register after the 16 bytes of `d`, starting from register 0 (slicing-by-4, 4 dependent steps)
+__device__ __forceinline__ uint32_t crc_piece(uint4 d, const uint32_t* __restrict__ sl) {
+  uint32_t c = d.x;
+  c = sl[768 + (c & 0xff)] ^ sl[512 + ((c >> 8) & 0xff)] ^ sl[256 + ((c >> 16) & 0xff)] ^ sl[c >> 24];
+  c ^= d.y;
+  c = sl[768 + (c & 0xff)] ^ sl[512 + ((c >> 8) & 0xff)] ^ sl[256 + ((c >> 16) & 0xff)] ^ sl[c >> 24];
+  c ^= d.z;
+  c = sl[768 + (c & 0xff)] ^ sl[512 + ((c >> 8) & 0xff)] ^ sl[256 + ((c >> 16) & 0xff)] ^ sl[c >> 24];
+  c ^= d.w;
+  c = sl[768 + (c & 0xff)] ^ sl[512 + ((c >> 8) & 0xff)] ^ sl[256 + ((c >> 16) & 0xff)] ^ sl[c >> 24];
+  return c;
+}
+// register * constant by 4 byte-indexed lookups
+__device__ __forceinline__ uint32_t crc_constmul(uint32_t u, const uint32_t* __restrict__ mt) {
+  return mt[u & 0xff] ^ mt[256 + ((u >> 8) & 0xff)] ^ mt[512 + ((u >> 16) & 0xff)] ^ mt[768 + (u >> 24)];
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic table kernel.
+//
+// Work item = (stripe, segment); a segment is tiles_per_seg tiles of NT*16 bytes of every shard.
+// Persistent CTAs walk the items; per item, thread `tid` owns the 16-byte column
+// [seg_start + t*TILE + 16*tid, +16) of every shard for t = 0..T-1:
+//   * loads the column of each input shard with one coalesced 128-bit access,
+//   * looks every byte up in a per-input 256-entry shared-memory table whose 32-bit entries
+//     pack the products for up to 4 outputs (one lookup per input byte, XOR accumulate),
+//   * unpacks the 16 accumulators into 4 output pieces and stores (or compares) them,
+//   * optionally advances a per-shard CRC register: piece remainder by slicing-by-4, Horner
+//     step (multiply by x^(8*TILE)) between pieces, so bytes are checksummed while in registers.
+// Tables are replicated R times (copy = lane % R) to cut bank conflicts; R is the largest
+// power of two <= 16 that fits next to the CRC state in shared memory.
+// ------------------------------------------------------------------------------------------
+template <int R, bool CRC>
+__global__ void __launch_bounds__(kTabThreads, 1) rs_tab_kernel(const TabParams p, const int n_crc_slots) {
+  constexpr int NT = kTabThreads;
+  constexpr int NW = NT / 32;
+  extern __shared__ __align__(128) uint8_t smem[];
+
+  // ---- shared memory carve-up ----
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);                       // 16 B
+  GfDeviceTables* gf_s = reinterpret_cast<GfDeviceTables*>(smem + 16);     // 768 B
+  Pattern* pat_s = reinterpret_cast<Pattern*>(smem + 16 + sizeof(GfDeviceTables));
+  size_t off = 16 + sizeof(GfDeviceTables) + sizeof(Pattern);
+  uint32_t* crc_sl = nullptr;   // slice[4][256]
+  uint32_t* crc_sh = nullptr;   // shift_tile[4][256]
+  uint32_t* crc_kt = nullptr;   // kthread[NT]
+  uint32_t* crc_st = nullptr;   // [n_crc_slots][NT]
+  uint32_t* crc_red = nullptr;  // [n_crc_slots][NW]
+  if (CRC) {
+    crc_sl = reinterpret_cast<uint32_t*>(smem + off);
+    crc_sh = crc_sl + 1024;
+    crc_kt = crc_sh + 1024;
+    off += (2048 + 1024) * 4;   // slice + shift + kthread[1024] are contiguous in CrcDeviceTables
+    crc_st = reinterpret_cast<uint32_t*>(smem + off);
+    off += (size_t)n_crc_slots * NT * 4;
+    crc_red = reinterpret_cast<uint32_t*>(smem + off);
+    off += (size_t)n_crc_slots * NW * 4;
+    off = (off + 127) & ~(size_t)127;
+  }
+  uint32_t* tab = reinterpret_cast<uint32_t*>(smem + off);   // [n_in][256][R]
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane % R;
+
+  // ---- stage the constant tables with TMA bulk copies ----
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t bytes = sizeof(GfDeviceTables) + (CRC ? (2048 + 1024) * 4 : 0);
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(gf_s, p.gf, sizeof(GfDeviceTables), bar);
+    if (CRC) bulk_g2s(crc_sl, p.crc, (2048 + 1024) * 4, bar);
+  }
+  mbar_wait(bar, 0);
+  const uint32_t poly = CRC ? p.crc->poly : 0;
+
+  if (CRC)
+    for (int i = tid; i < n_crc_slots * NT; i += NT) crc_st[i] = 0;
+
+  uint32_t cur_pattern = 0xFFFFFFFFu;
+  const uint32_t n_items = p.n_stripes * p.n_seg;
+  const size_t seg_bytes = (size_t)p.tiles_per_seg * kTabTile;
+
+  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t s = item / p.n_seg, seg = item - s * p.n_seg;
+    const uint32_t pat_id = p.pattern_of_stripe ? p.pattern_of_stripe[s] : 0u;
+    if (pat_id != cur_pattern) {
+      __syncthreads();   // everyone finished with the old tables / pattern
+      cur_pattern = pat_id;
+      const uint4* src = reinterpret_cast<const uint4*>(p.patterns + pat_id);
+      uint4* dst = reinterpret_cast<uint4*>(pat_s);
+      for (int i = tid; i < (int)(sizeof(Pattern) / 16); i += NT) dst[i] = src[i];
+      __syncthreads();
+      const int n_in = pat_s->n_in, n_out = pat_s->n_out;
+      for (int idx = tid; idx < n_in * 256; idx += NT) {
+        const int c = idx >> 8, v = idx & 255;
+        uint32_t e = 0;
+        if (v) {
+          const int lv = gf_s->log[v];
+          for (int r = 0; r < n_out; r++) {
+            const int co = pat_s->coef[r][c];
+            if (co) e |= (uint32_t)gf_s->exp[gf_s->log[co] + lv] << (8 * r);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < R; q++) tab[(size_t)idx * R + q] = e;
+      }
+      __syncthreads();
+    }
+    const int n_in = pat_s->n_in, n_out = pat_s->n_out;
+    const bool crc_in = CRC && pat_s->crc_in;
+    uint8_t* sbase = p.base + (size_t)s * p.stripe_pitch;
+    const uint32_t T = (seg == p.n_seg - 1) ? p.tiles_last : p.tiles_per_seg;
+    const size_t seg_start = (size_t)seg * seg_bytes;
+    bool bad = false;
+
+    for (uint32_t t = 0; t < T; t++) {
+      const size_t col = seg_start + (size_t)t * kTabTile + (size_t)tid * kPiece;
+      const bool live = col < p.shard_len;
+      const int tail = (live && col + kPiece > p.shard_len) ? (int)(p.shard_len - col) : 0;
+      uint32_t acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) acc[i] = 0;
+
+      constexpr int CH = 6;
+      for (int c0 = 0; c0 < n_in; c0 += CH) {
+        uint4 d[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+          d[i] = make_uint4(0, 0, 0, 0);
+          if (c0 + i < n_in && live) d[i] = ldg_stream(sbase + (size_t)pat_s->in_slot[c0 + i] * p.shard_pitch + col);
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+          if (c0 + i < n_in) {
+            if (tail) d[i] = keep_head(d[i], tail);
+            const uint32_t* tb = tab + (size_t)(c0 + i) * 256 * R + g;
+            const uint32_t w[4] = {d[i].x, d[i].y, d[i].z, d[i].w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              acc[q * 4 + 0] ^= tb[(w[q] & 0xff) * R];
+              acc[q * 4 + 1] ^= tb[((w[q] >> 8) & 0xff) * R];
+              acc[q * 4 + 2] ^= tb[((w[q] >> 16) & 0xff) * R];
+              acc[q * 4 + 3] ^= tb[(w[q] >> 24) * R];
+            }
+            if (crc_in) {
+              uint32_t* st = crc_st + (size_t)(c0 + i) * NT + tid;
+              *st = crc_constmul(*st, crc_sh) ^ crc_piece(d[i], crc_sl);
+            }
+          }
+        }
+      }
+      // unpack: output r, word q = byte r of acc[q*4 + 0..3]
+      for (int r = 0; r < n_out; r++) {
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const uint32_t lo = __byte_perm(acc[q * 4 + 0], acc[q * 4 + 1], 0x0040 | r | (r << 4));
+          const uint32_t hi = __byte_perm(acc[q * 4 + 2], acc[q * 4 + 3], 0x0040 | r | (r << 4));
+          o[q] = __byte_perm(lo, hi, 0x5410);
+        }
+        const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
+        uint8_t* optr = sbase + (size_t)pat_s->out_slot[r] * p.shard_pitch + col;
+        if (p.mode == 0) {
+          if (live) stg_stream(optr, ov);
+        } else if (live) {
+          uint4 e = ldg_stream(optr);
+          if (tail) e = keep_head(e, tail);
+          bad |= (e.x != ov.x) | (e.y != ov.y) | (e.z != ov.z) | (e.w != ov.w);
+        }
+        if (CRC) {
+          uint32_t* st = crc_st + (size_t)((crc_in ? n_in : 0) + r) * NT + tid;
+          *st = crc_constmul(*st, crc_sh) ^ crc_piece(ov, crc_sl);
+        }
+      }
+    }
+
+    if (p.mode == 1 && bad) atomicExch(&p.mismatch[s], 1);
+
+    if (CRC && p.crc_part) {
+      // Align every thread's partial to the end of the (virtual) segment, XOR-reduce over the CTA.
+      const int nq = (crc_in ? n_in : 0) + n_out;
+      const uint32_t kt = crc_kt[tid];
+      for (int q = 0; q < nq; q++) {
+        uint32_t u = gf32_mul(crc_st[(size_t)q * NT + tid], kt, poly);
+        crc_st[(size_t)q * NT + tid] = 0;
+        u = __reduce_xor_sync(0xffffffffu, u);
+        if (lane == 0) crc_red[q * NW + warp] = u;
+      }
+      __syncthreads();
+      if (tid < nq) {
+        uint32_t u = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; w2++) u ^= crc_red[tid * NW + w2];
+        const int slot = (crc_in && tid < n_in) ? pat_s->in_slot[tid] : pat_s->out_slot[tid - (crc_in ? n_in : 0)];
+        p.crc_part[((size_t)s * p.n_slots + slot) * p.n_seg + seg] = u;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+static size_t tab_smem_bytes(int n_in, int R, bool with_crc, int n_crc_slots) {
+  size_t off = 16 + sizeof(GfDeviceTables) + sizeof(Pattern);
+  if (with_crc) {
+    off += (2048 + 1024) * 4;
+    off += (size_t)n_crc_slots * kTabThreads * 4;
+    off += (size_t)n_crc_slots * (kTabThreads / 32) * 4;
+    off = (off + 127) & ~(size_t)127;
+  }
+  off += (size_t)n_in * 256 * R * 4;
+  return off;
+}
+
+int tab_pick_replication(int n_in, bool with_crc, int n_crc_slots, size_t smem_limit, size_t* smem_bytes) {
+  for (int R = 16; R >= 1; R >>= 1) {
+    size_t need = tab_smem_bytes(n_in, R, with_crc, n_crc_slots);
+    if (need <= smem_limit) {
+      if (smem_bytes) *smem_bytes = need;
+      return R;
+    }
+  }
+  return 0;
+}
+
+template <int R, bool CRC>
+static cudaError_t tab_set_attr(size_t limit) {
+  return cudaFuncSetAttribute(rs_tab_kernel<R, CRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+}
+
+cudaError_t tab_configure(size_t* smem_limit_out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  int optin = 0;
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  size_t limit = (size_t)optin;
+#define CUBEEC_SET(R)                                                      \
+  if ((e = tab_set_attr<R, false>(limit)) != cudaSuccess) return e;        \
+  if ((e = tab_set_attr<R, true>(limit)) != cudaSuccess) return e;
+  CUBEEC_SET(16) CUBEEC_SET(8) CUBEEC_SET(4) CUBEEC_SET(2) CUBEEC_SET(1)
+#undef CUBEEC_SET
+  if (smem_limit_out) *smem_limit_out = limit;
+  return cudaSuccess;
+}
+
+cudaError_t launch_tab(const TabParams& p, int R, bool with_crc, int n_crc_slots, size_t smem_bytes, int grid,
+                       cudaStream_t stream) {
+#define CUBEEC_LAUNCH(RR)                                                                              \
+  case RR:                                                                                             \
+    if (with_crc) rs_tab_kernel<RR, true><<<grid, kTabThreads, smem_bytes, stream>>>(p, n_crc_slots);  \
+    else rs_tab_kernel<RR, false><<<grid, kTabThreads, smem_bytes, stream>>>(p, n_crc_slots);          \
+    break;
+  switch (R) {
+    CUBEEC_LAUNCH(16) CUBEEC_LAUNCH(8) CUBEEC_LAUNCH(4) CUBEEC_LAUNCH(2) CUBEEC_LAUNCH(1)
+    default: return cudaErrorInvalidValue;
+  }
+#undef CUBEEC_LAUNCH
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// CRC finalize: Horner over the per-segment remainders of one (stripe, slot), then the
+// init / xorout terms:  crc = ~( R(data) ^ 0xFFFFFFFF * x^(8 len) ).
+// ------------------------------------------------------------------------------------------
+__global__ void crc_finalize_kernel(const CrcFinalizeParams p) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= p.n_units) return;
+  if (p.slot_enable && !p.slot_enable[u % p.n_slots]) return;
+  const uint32_t* part = p.crc_part + (size_t)u * p.n_seg;
+  uint32_t r = 0;
+  for (uint32_t j = 0; j < p.n_seg; j++) {
+    if (j) r = gf32_mul(r, (j == p.n_seg - 1) ? p.x_last : p.x_full, p.poly);
+    r ^= part[j];
+  }
+  r = gf32_mul(r, p.fix, p.poly);
+  p.out[u] = ~(r ^ p.init_term);
+}
+
+cudaError_t launch_crc_finalize(const CrcFinalizeParams& p, cudaStream_t stream) {
+  const int nt = 128;
+  crc_finalize_kernel<<<(p.n_units + nt - 1) / nt, nt, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone CRC over arbitrary byte ranges ("units") of flat buffers: the crc32block
+// payload blocks (65532 B, aligned to nothing) and whole buffers.  One CTA per unit at a time.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTabThreads) crc_range_kernel(const CrcRangeParams p) {
+  constexpr int NT = kTabThreads, NW = NT / 32;
+  __shared__ __align__(16) uint32_t sl[1024];
+  __shared__ __align__(16) uint32_t sh[1024];
+  __shared__ uint32_t red[NW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 1024; i += NT) {
+    sl[i] = (&p.crc->slice[0][0])[i];
+    sh[i] = (&p.crc->shift_tile[0][0])[i];
+  }
+  const uint32_t kt = p.crc->kthread[tid];
+  const uint32_t poly = p.crc->poly;
+  __syncthreads();
+  const uint64_t n_units = (uint64_t)p.n_buffers * p.units_per_buffer;
+  for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const uint32_t b = (uint32_t)(unit / p.units_per_buffer), u = (uint32_t)(unit - (uint64_t)b * p.units_per_buffer);
+    const uint8_t* buf = p.base + (size_t)b * p.pitch;
+    const size_t a = (size_t)u * p.block;
+    const size_t e = (a + p.block < p.len) ? a + p.block : p.len;
+    // pieces are 16-byte aligned in the address space (base and pitch are 16-aligned)
+    const size_t a_al = a & ~(size_t)15;
+    const uint32_t T = (uint32_t)((e - a_al + kTabTile - 1) / kTabTile);
+    uint32_t st = 0;
+    for (uint32_t t = 0; t < T; t++) {
+      const size_t col = a_al + (size_t)t * kTabTile + (size_t)tid * kPiece;
+      uint4 d = make_uint4(0, 0, 0, 0);
+      if (col < e) {
+        d = ldg_stream(buf + col);
+        if (col < a) d = drop_head(d, (int)(a - col));
+        if (col + kPiece > e) d = keep_head(d, (int)(e - col));
+      }
+      st = crc_constmul(st, sh) ^ crc_piece(d, sl);
+    }
+    uint32_t v = gf32_mul(st, kt, poly);
+    v = __reduce_xor_sync(0xffffffffu, v);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t r = 0;
+      for (int w = 0; w < NW; w++) r ^= red[w];
+      // virtual end = a_al + T*TILE; remove the z zero bytes behind the real end e
+      const uint64_t z = (uint64_t)a_al + (uint64_t)T * kTabTile - e;
+      const uint64_t ord = 0xFFFFFFFFull;
+      const uint64_t neg = (ord - (8 * z) % ord) % ord;
+      r = gf32_mul(r, gf32_xpow(neg, poly), poly);
+      const uint32_t init_term = gf32_mul(0xFFFFFFFFu, gf32_xpow(8ull * (e - a), poly), poly);
+      p.out[unit] = ~(r ^ init_term);
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_crc_ranges(const CrcRangeParams& p, int grid, cudaStream_t stream) {
+  crc_range_kernel<<<grid, kTabThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// whole = crc32_combine over the units of a buffer: crc(A||B) = crc(A)*x^(8|B|) ^ crc(B)
+__global__ void crc_combine_kernel(const uint32_t* unit_crc, uint32_t n_buffers, uint32_t units, uint32_t len,
+                                   uint32_t block, uint32_t poly, uint32_t* whole) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_buffers) return;
+  const uint32_t x_block = gf32_xpow(8ull * block, poly);
+  const uint32_t last_len = len - (units - 1) * block;
+  const uint32_t x_last = gf32_xpow(8ull * last_len, poly);
+  uint32_t acc = 0;
+  for (uint32_t u = 0; u < units; u++) {
+    if (u) acc = gf32_mul(acc, (u == units - 1) ? x_last : x_block, poly);
+    acc ^= unit_crc[(size_t)b * units + u];
+  }
+  whole[b] = acc;
+}
+
+cudaError_t launch_crc_combine(const uint32_t* unit_crc, uint32_t n_buffers, uint32_t units, uint32_t len,
+                               uint32_t block, uint32_t poly, uint32_t* whole, cudaStream_t stream) {
+  const int nt = 64;
+  crc_combine_kernel<<<(n_buffers + nt - 1) / nt, nt, 0, stream>>>(unit_crc, n_buffers, units, len, block, poly,
+                                                                   whole);
+  return cudaGetLastError();
+}
+
+__global__ void invert_flags_kernel(int32_t* flags, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = flags[i] ? 0 : 1;
+}
+cudaError_t launch_invert_flags(int32_t* flags, size_t n, cudaStream_t stream) {
+  const int nt = 256;
+  invert_flags_kernel<<<(unsigned)((n + nt - 1) / nt), nt, 0, stream>>>(flags, n);
+  return cudaGetLastError();
+}
+
+}  // namespace cbe

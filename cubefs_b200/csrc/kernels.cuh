@@ -1,0 +1,102 @@
+// kernels.cuh -- device-side data structures and launch wrappers of libcubeec (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace cbe {
+
+constexpr int kMaxIn = 128;   // inputs (survivor / data shards) one pass can read
+constexpr int kMaxOut = 4;    // outputs one pass produces (one packed u32 table entry)
+constexpr int kTabThreads = 512;
+constexpr int kPiece = 16;    // bytes per thread per tile: one 128-bit access
+constexpr int kTabTile = kTabThreads * kPiece;
+
+// One coding "pattern": which shard slots are read, which are produced, and the coefficients.
+// Encode has one pattern per pass; reconstruct has one per distinct erasure pattern.
+struct alignas(16) Pattern {
+  uint8_t n_in, n_out;
+  uint8_t crc_in;   // also checksum the inputs (first pass of encode)
+  uint8_t pad;
+  uint8_t out_slot[kMaxOut];
+  uint8_t in_slot[kMaxIn];
+  uint8_t coef[kMaxOut][kMaxIn];   // coef[r][c]: out r += coef * in c
+  uint8_t pad2[8];
+};
+static_assert(sizeof(Pattern) % 16 == 0, "Pattern must be bulk-copyable");
+
+// Field tables staged into shared memory by cp.async.bulk (TMA 1-D).
+struct alignas(16) GfDeviceTables {
+  uint8_t log[256];
+  uint8_t exp[512];
+};
+
+// CRC tables for a fixed thread count / tile stride.
+struct alignas(16) CrcDeviceTables {
+  uint32_t slice[4][256];      // slicing-by-4 byte tables
+  uint32_t shift_tile[4][256]; // register * x^(8*tile bytes): Horner step between a thread's pieces
+  uint32_t kthread[1024];      // x^(8*(tile - 16*(tid+1))): aligns a thread's partial to the tile end
+  uint32_t poly;
+  uint32_t pad[3];
+};
+
+struct TabParams {
+  uint8_t* base;
+  size_t stripe_pitch;
+  size_t shard_pitch;
+  uint32_t shard_len;
+  uint32_t n_stripes;
+  uint32_t n_seg;            // segments per shard
+  uint32_t tiles_per_seg;    // tiles in a full segment
+  uint32_t tiles_last;       // tiles in the last segment
+  uint32_t n_slots;          // shard slots per stripe (k+m[+l])
+  const Pattern* patterns;
+  const uint32_t* pattern_of_stripe;   // nullptr -> pattern 0 for every stripe
+  int mode;                  // 0 = store outputs, 1 = compare with stored outputs
+  int32_t* mismatch;         // compare mode: [n_stripes], set to 1 on any difference
+  uint32_t* crc_part;        // [n_stripes][n_slots][n_seg] raw segment remainders, or nullptr
+  const GfDeviceTables* gf;
+  const CrcDeviceTables* crc;
+};
+
+struct CrcFinalizeParams {
+  const uint32_t* crc_part;  // [n_units][n_seg]
+  uint32_t n_units;          // n_stripes * n_slots
+  uint32_t n_slots;
+  uint32_t n_seg;
+  uint32_t x_full;           // x^(8*full segment bytes)
+  uint32_t x_last;           // x^(8*virtual bytes of the last segment)
+  uint32_t fix;              // x^(-8*zero padding after the real end)
+  uint32_t init_term;        // 0xFFFFFFFF * x^(8*len)
+  uint32_t poly;
+  const uint8_t* slot_enable;   // [n_slots] or nullptr (all)
+  uint32_t* out;             // [n_units]
+};
+
+// Smallest table replication (copies per entry, power of two <= 16) that fits.
+int tab_pick_replication(int n_in, bool with_crc, int n_crc_slots, size_t smem_limit, size_t* smem_bytes);
+cudaError_t launch_tab(const TabParams& p, int replication, bool with_crc, int n_crc_slots,
+                       size_t smem_bytes, int grid, cudaStream_t stream);
+cudaError_t launch_crc_finalize(const CrcFinalizeParams& p, cudaStream_t stream);
+cudaError_t tab_configure(size_t* smem_limit_out);   // sets max dynamic smem attributes
+
+cudaError_t launch_invert_flags(int32_t* flags, size_t n, cudaStream_t stream);   // flags[i] = !flags[i]
+
+// Stand-alone CRC over byte ranges of flat buffers (crc32 / crc32block surface).
+struct CrcRangeParams {
+  const uint8_t* base;       // buffer b at base + b*pitch
+  size_t pitch;
+  uint32_t n_buffers;
+  uint32_t len;              // bytes per buffer
+  uint32_t block;            // bytes per CRC unit (block payload); len if whole only
+  uint32_t units_per_buffer; // ceil(len/block)
+  const CrcDeviceTables* crc;
+  uint32_t* out;             // [n_buffers][units_per_buffer] final CRCs of each unit
+};
+cudaError_t launch_crc_ranges(const CrcRangeParams& p, int grid, cudaStream_t stream);
+// whole[b] = combine(units of buffer b); device-side Horner over the per-unit CRCs.
+cudaError_t launch_crc_combine(const uint32_t* unit_crc, uint32_t n_buffers, uint32_t units_per_buffer,
+                               uint32_t len, uint32_t block, uint32_t poly, uint32_t* whole,
+                               cudaStream_t stream);
+
+}  // namespace cbe

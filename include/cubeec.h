@@ -1,0 +1,181 @@
+/*
+ * cubeec.h -- C-ABI of libcubeec: the B200-native Reed-Solomon + CRC32 engine that
+ * drops in behind CubeFS BlobStore's erasure-coding seam.
+ *
+ * What it replaces (paths relative to the cubefs tree; RS/ =
+ * vendor/github.com/klauspost/reedsolomon v1.11.7, BS/ = blobstore):
+ *
+ *   The `engine reedsolomon.Encoder` field of ec.encoder / ec.lrcEncoder
+ *   (BS/common/ec/encoder.go:71-75, lrcencoder.go:28-33), i.e. the six methods CubeFS
+ *   calls on it -- Encode, Verify, Reconstruct, ReconstructData (device work, below)
+ *   and Split, Join (pure slicing, stay in Go).  Plus the whole-shard and
+ *   per-64KiB-block CRC32-IEEE passes of the shard write/read path
+ *   (BS/access/stream/stream_put.go:265-269, BS/blobnode/core/storage/datafile.go:337-342,
+ *   BS/common/crc32block/block.go:38-49).
+ *
+ * Conventions
+ *   - Plain C types only; no pointer is retained after a call returns (cgo rule).
+ *   - Every function returns 0 on success or one of the CUBEEC_ERR_* codes; the Go shim
+ *     maps them onto the existing error VALUES (reedsolomon.ErrTooFewShards, ...), see
+ *     INTEGRATION.md.  Validation order mirrors the reference (shard count, then
+ *     checkShards RS/reedsolomon.go:1314-1327).
+ *   - A shard list is Go's [][]byte flattened: `shards[i]` + `lens[i]`; len 0 == missing
+ *     (nil or [:0]).  The caller owns all memory; parity / regenerated shards are written in
+ *     place.  For a missing shard the caller passes a buffer with room for the shard size
+ *     (the Go shim allocates when cap < shardSize, as RS/reedsolomon.go:1514-1518 does).
+ *   - All entry points are thread-safe; a handle is immutable after create.
+ *   - There is NO CPU fallback: every compute entry point fails with CUBEEC_ERR_NO_DEVICE
+ *     if no CUDA device is usable.
+ */
+#ifndef CUBEEC_H
+#define CUBEEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  CUBEEC_OK = 0,
+  CUBEEC_ERR_INV_SHARD_NUM = 1,        /* reedsolomon.ErrInvShardNum        RS/reedsolomon.go:204 */
+  CUBEEC_ERR_MAX_SHARD_NUM = 2,        /* reedsolomon.ErrMaxShardNum        RS/reedsolomon.go:209 */
+  CUBEEC_ERR_TOO_FEW_SHARDS = 3,       /* reedsolomon.ErrTooFewShards       RS/reedsolomon.go:601 */
+  CUBEEC_ERR_SHARD_NO_DATA = 4,        /* reedsolomon.ErrShardNoData        RS/reedsolomon.go:1305 */
+  CUBEEC_ERR_SHARD_SIZE = 5,           /* reedsolomon.ErrShardSize          RS/reedsolomon.go:1309 */
+  CUBEEC_ERR_SHORT_DATA = 6,           /* reedsolomon.ErrShortData          RS/reedsolomon.go:1556 */
+  CUBEEC_ERR_RECONSTRUCT_REQUIRED = 7, /* reedsolomon.ErrReconstructRequired RS/reedsolomon.go:1636 */
+  CUBEEC_ERR_SINGULAR = 8,             /* errSingular                       RS/matrix.go:184 */
+  CUBEEC_ERR_INVALID_ARG = 9,
+  CUBEEC_ERR_NO_DEVICE = 10,           /* no usable CUDA device / extension: fail loudly */
+  CUBEEC_ERR_CUDA = 11,                /* a CUDA call failed; see cubeec_last_error() */
+  CUBEEC_ERR_UNSUPPORTED = 12          /* geometry outside what the engine supports */
+};
+
+enum { CUBEEC_CRC_IEEE = 0, CUBEEC_CRC_CASTAGNOLI = 1 };
+
+typedef struct cubeec cubeec_t;
+
+/* ---- process-wide ---------------------------------------------------------------- */
+
+/* Select the CUDA devices the engine may use (default: device 0 only).  With n > 1 the
+ * batched entry points partition stripes contiguously over the devices;
+ * the coding matrices are the only shared state.  May be called once, before any handle
+ * is created.  devices == NULL -> 0..n-1. */
+int cubeec_init(const int* devices, int n_devices);
+int cubeec_device_count(void);
+const char* cubeec_strerror(int code);
+/* Thread-local detail string of the last CUBEEC_ERR_CUDA on this thread. */
+const char* cubeec_last_error(void);
+
+/* Pinned host memory for zero-staging H2D/D2H (optional; any host pointer is accepted
+ * by the host entry points, pinned ones are DMA'd directly). */
+int cubeec_host_alloc(size_t bytes, void** out);
+int cubeec_host_free(void* p);
+int cubeec_host_register(void* p, size_t bytes);
+int cubeec_host_unregister(void* p);
+
+/* ---- handle ---------------------------------------------------------------------- */
+
+/* reedsolomon.New(k, m) with default options (BS/common/ec/encoder.go:86,95):
+ * parity_rows == NULL -> the systematic Vandermonde-derived matrix of
+ * RS/reedsolomon.go:220-244 (bit-exact with klauspost); otherwise m x k row-major bytes
+ * (the WithCustomMatrix case, RS/reedsolomon.go:440-456). */
+int cubeec_create(int k, int m, const uint8_t* parity_rows, cubeec_t** out);
+void cubeec_destroy(cubeec_t* h);
+int cubeec_k(const cubeec_t* h);
+int cubeec_m(const cubeec_t* h);
+/* Full (k+m) x k generator, identity on top. */
+int cubeec_matrix(const cubeec_t* h, uint8_t* out);
+/* The decode rows the engine uses for a presence pattern: valid[k] = the first k present
+ * indices, rows = k x k inverse of those generator rows (RS/reedsolomon.go:1453-1501). */
+int cubeec_decode_matrix(const cubeec_t* h, const uint8_t* present /* k+m */, int* valid, uint8_t* rows);
+
+/* ---- single stripe, host scatter pointers (the reedsolomon.Encoder subset) ---------- */
+
+/* reedSolomon.Encode (RS/reedsolomon.go:609-625) = ec.encoder.Encode's engine call
+ * (BS/common/ec/encoder.go:118).  n must be k+m.  Parity shards are overwritten, data
+ * shards are only read.  crc_out (optional, k+m entries) receives CRC32 of every shard
+ * computed in the same pass (replaces BS/access/stream/stream_put.go:265-269). */
+int cubeec_encode(cubeec_t* h, uint8_t* const* shards, const size_t* lens, int n,
+                  uint32_t* crc_out, int crc_poly);
+
+/* reedSolomon.Verify (RS/reedsolomon.go:770-784): *ok = 1 iff parity matches. */
+int cubeec_verify(cubeec_t* h, uint8_t* const* shards, const size_t* lens, int n, int* ok);
+
+/* reedSolomon.Reconstruct / ReconstructData (RS/reedsolomon.go:1368-1388,1407-1552).
+ * Missing = lens[i] == 0.  data_only != 0 leaves missing parity missing.
+ * filled (optional, n bytes) is set to 1 for every shard that was regenerated.
+ * crc_out (optional, n entries): CRC32 of the regenerated shards (others untouched). */
+int cubeec_reconstruct(cubeec_t* h, uint8_t* const* shards, const size_t* lens, int n,
+                       int data_only, uint8_t* filled, uint32_t* crc_out, int crc_poly);
+
+/* ---- batched, host memory ------------------------------------------------------------ */
+
+/* ec.Buffer layout (BS/common/ec/buf.go:23-35 + RS/reedsolomon.go:1618-1624): shard i of
+ * stripe s lives at base + s*stripe_pitch + i*shard_len, i < k+m.  Encodes every stripe.
+ * crc_out (optional): n_stripes*(k+m) whole-shard CRCs.  blockcrc_out (optional):
+ * n_stripes*(k+m)*ceil(shard_len/block_payload) per-block CRCs in crc32block order
+ * (block_payload = 65532 for the default 64 KiB block, BS/common/crc32block/util.go:44-46). */
+int cubeec_encode_contig(cubeec_t* h, uint8_t* base, size_t shard_len, size_t n_stripes,
+                         size_t stripe_pitch, uint32_t* crc_out, uint32_t* blockcrc_out,
+                         size_t block_payload, int crc_poly);
+
+/* One stripe of a batched reconstruct: the repair loop of
+ * BS/blobnode/worker_slice_recover.go:822-885 (one entry per bid). */
+typedef struct cubeec_stripe {
+  uint8_t* const* shards;   /* k+m pointers */
+  const uint8_t* present;   /* k+m flags, 0 = regenerate this shard */
+  size_t shard_len;
+} cubeec_stripe_t;
+
+/* Reconstruct (+ optionally Verify, as the repair loop does at :871) a batch of stripes
+ * with independent erasure patterns and lengths.  verify_ok (optional, n entries). */
+int cubeec_reconstruct_batch(cubeec_t* h, const cubeec_stripe_t* stripes, size_t n_stripes,
+                             int data_only, int* verify_ok);
+
+/* ---- batched, device-resident (what bench.py's `value` times) ------------------------- */
+
+/* A stripe batch already in HBM: shard i of stripe s at d_base + s*stripe_pitch +
+ * i*shard_pitch; d_base 16-byte aligned, shard_pitch and stripe_pitch multiples of 16 and
+ * shard_pitch >= shard_len.  Bytes [shard_len, shard_pitch) of OUTPUT shards are zeroed.
+ * d_crc_out (optional, device): n_stripes*(k+m) CRCs.  stream: a cudaStream_t (NULL = the
+ * engine's own stream; the call then returns after the work completed). */
+int cubeec_dev_encode(cubeec_t* h, int device, void* d_base, size_t shard_len, size_t shard_pitch,
+                      size_t stripe_pitch, size_t n_stripes, uint32_t* d_crc_out, int crc_poly,
+                      void* stream);
+/* present: HOST array n_stripes*(k+m).  Regenerates every missing shard of every stripe in
+ * one fused pass (missing parity is produced directly from the survivors). */
+int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, size_t shard_len, size_t shard_pitch,
+                           size_t stripe_pitch, size_t n_stripes, const uint8_t* present,
+                           int data_only, void* stream);
+/* d_ok (device, n_stripes int32): 1 iff the stripe's parity matches. */
+int cubeec_dev_verify(cubeec_t* h, int device, const void* d_base, size_t shard_len, size_t shard_pitch,
+                      size_t stripe_pitch, size_t n_stripes, int32_t* d_ok, void* stream);
+
+/* ---- CRC32 ------------------------------------------------------------------------------ */
+
+/* crc32.ChecksumIEEE(p[:n]) on the GPU (host pointer). */
+int cubeec_crc32(const uint8_t* p, size_t n, int crc_poly, uint32_t* out);
+/* Per-block CRCs of the crc32block framing plus the whole-buffer CRC in one pass
+ * (datafile.Write computes both, BS/blobnode/core/storage/datafile.go:337-342).
+ * per_block: ceil(n/block_payload) entries (optional); whole: optional. */
+int cubeec_crc32_blocks(const uint8_t* p, size_t n, size_t block_payload, int crc_poly,
+                        uint32_t* per_block, uint32_t* whole);
+/* Device-resident variant over many equal-length buffers: buffer b at d_base + b*pitch. */
+int cubeec_dev_crc32(int device, const void* d_base, size_t len, size_t pitch, size_t n_buffers,
+                     size_t block_payload /* 0 = whole only */, int crc_poly,
+                     uint32_t* d_whole /* n_buffers or NULL */, uint32_t* d_blocks /* or NULL */,
+                     void* stream);
+
+/* ---- introspection (tests / bench) -------------------------------------------------------- */
+/* Kernels launched by this process so far (all devices). */
+uint64_t cubeec_kernel_launches(void);
+/* Name of the kernel variant the last dev_* call on this thread dispatched to. */
+const char* cubeec_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
