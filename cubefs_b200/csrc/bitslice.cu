@@ -1,0 +1,343 @@
+// bitslice.cu -- the bit-sliced RS encode kernel with fused CRC32 (sm_100a).
+//
+// The hot kernel of BASELINE config C2 (RS(12,4) encode + CRC32 of all shards in one HBM pass).
+// Replaces reedSolomon.Encode's SIMD loop (RS/reedsolomon.go:609-625,897-1134; kernels
+// RS/galois_gen_amd64.s) and the per-shard crc32.ChecksumIEEE pass of
+// blobstore/access/stream/stream_put.go:265-269.
+//
+// Why bit-sliced: B200 has no byte-shuffle (PSHUFB) or GF affine instruction, and a table lookup
+// per input byte saturates the shared-memory pipe at about half of HBM speed (kernels.cu).  Here a
+// thread turns 32 bytes of a shard (one 256-bit load) into 8 bit-planes with a SWAR 8x8 bit
+// transpose (12 delta swaps), and multiplication by the (compile-time) matrix coefficients becomes
+// a fixed XOR network on planes: 3-input XORs = one LOP3 each, no memory traffic.  The CRC runs
+// on the same registers before the transpose: slicing-by-4 over the 8 words with lane-private
+// (conflict-free) copies of the tables in shared memory, one PRMT to form each lookup address.
+// Per thread the CRC registers advance Horner-style over the tiles; partial remainders are
+// aligned and XOR-reduced once per work item and finished by crc_finalize_kernel.
+#include <type_traits>
+
+#include "bs_net_gen.cuh"
+#include "kernels.cuh"
+
+namespace cbe {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <int IMM>
+__device__ __forceinline__ uint32_t lds32_off(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// 8x8 bit transpose across 8 words, independently in each of the 4 byte lanes (an involution):
+// afterwards word j holds bit j of all 32 bytes.  12 delta swaps = 24 LOP3 + 12 right shifts
+// (ALU pipe) + 12 left shifts written as multiplies (FMA pipe).
+// d = (a & MASK) | (b & ~MASK) in ONE LOP3 (lut 0xE4 with the mask as the immediate operand)
+template <uint32_t MASK>
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "n"(MASK));
+  return d;
+}
+template <int S, uint32_t MASK>
+__device__ __forceinline__ void delta_swap(uint32_t& a, uint32_t& b) {
+  const uint32_t na = bitsel<MASK>(a, b * (1u << S));
+  const uint32_t nb = bitsel<MASK>(a >> S, b);
+  a = na;
+  b = nb;
+}
+__device__ __forceinline__ void bit_transpose8(uint32_t (&w)[8]) {
+  delta_swap<4, 0x0f0f0f0fu>(w[0], w[4]);
+  delta_swap<4, 0x0f0f0f0fu>(w[1], w[5]);
+  delta_swap<4, 0x0f0f0f0fu>(w[2], w[6]);
+  delta_swap<4, 0x0f0f0f0fu>(w[3], w[7]);
+  delta_swap<2, 0x33333333u>(w[0], w[2]);
+  delta_swap<2, 0x33333333u>(w[1], w[3]);
+  delta_swap<2, 0x33333333u>(w[4], w[6]);
+  delta_swap<2, 0x33333333u>(w[5], w[7]);
+  delta_swap<1, 0x55555555u>(w[0], w[1]);
+  delta_swap<1, 0x55555555u>(w[2], w[3]);
+  delta_swap<1, 0x55555555u>(w[4], w[5]);
+  delta_swap<1, 0x55555555u>(w[6], w[7]);
+}
+
+__device__ __forceinline__ uint32_t gf32_mul_dev(uint32_t a, uint32_t b, uint32_t poly) {
+  uint32_t r = 0;
+#pragma unroll 8
+  for (int i = 0; i < 32; i++) {
+    r ^= a & (uint32_t)((int32_t)b >> 31);
+    b <<= 1;
+    a = (a >> 1) ^ (poly & (0u - (a & 1u)));
+  }
+  return r;
+}
+
+// compile-time dispatch on the shard index
+template <class Net, int C, int K>
+struct ApplyAt {
+  static __device__ __forceinline__ void run(int c, const uint32_t (&w)[8], uint32_t (&acc)[8 * Net::M]) {
+    if (c == C) Net::template apply<C>(w, acc);
+    else ApplyAt<Net, C + 1, K>::run(c, w, acc);
+  }
+};
+template <class Net, int K>
+struct ApplyAt<Net, K, K> {
+  static __device__ __forceinline__ void run(int, const uint32_t (&)[8], uint32_t (&)[8 * Net::M]) {}
+};
+
+}  // namespace
+
+template <int K, int M, bool CRC>
+__global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) {
+  using Net = BsNet<K, M>;
+  constexpr int NT = kBsThreads, NW = NT / 32;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- shared memory: [misc: mbarrier | fold tables (4 copies) | kthread | reduction] ... [64K-aligned slice image]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* fold_s = reinterpret_cast<uint32_t*>(smem + 64);                       // [4][256][kBsFoldCopies]
+  uint32_t* kth_s = fold_s + 4 * 256 * kBsFoldCopies;                              // [NT]
+  uint32_t* red_s = kth_s + NT;                                                    // [(K+M)][NW]
+  const uint32_t base_addr = smem_addr(smem);
+  uint32_t tab_addr = 0;   // shared address of the slice image
+  if (CRC) {
+    tab_addr = (base_addr + (uint32_t)(64 + 4 * 256 * kBsFoldCopies * 4 + NT * 4 + (K + M) * NW * 4) + 65535u) & ~65535u;
+    uint8_t* tab_ptr = smem + (tab_addr - base_addr);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // TMA 1-D bulk copies: the replicated slicing tables, two 64 KiB halves
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+                   "r"((uint32_t)kBsSliceImageBytes)
+                   : "memory");
+      for (int h = 0; h < 2; h++)
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_addr(tab_ptr + h * 65536)),
+            "l"(reinterpret_cast<const uint8_t*>(p.slice_image) + h * 65536), "r"(65536u), "r"(smem_addr(bar))
+            : "memory");
+    }
+    for (int i = tid; i < 4 * 256; i += NT) {
+      const uint32_t v = p.fold_tables[i];
+#pragma unroll
+      for (int q = 0; q < kBsFoldCopies; q++) fold_s[i * kBsFoldCopies + q] = v;
+    }
+    kth_s[tid] = p.kthread[tid];
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(smem_addr(bar))
+          : "memory");
+    }
+    __syncthreads();
+  }
+  // lane-private lookup base: byte0 = lane*4, byte2 = bits 16..23 of the table address
+  const uint32_t lane_base = tab_addr | (uint32_t)(lane * 4);
+  const uint32_t fold_lane = smem_addr(fold_s) + (uint32_t)((lane & (kBsFoldCopies - 1)) * 4);
+
+  // one slicing-by-4 step: register after absorbing the 4 bytes of y (= state ^ data word)
+  auto slice4 = [&](uint32_t y) -> uint32_t {
+    const uint32_t a0 = prmt(y, lane_base, 0x7604u);   // (table hi) | byte0 << 8 | lane*4
+    const uint32_t a1 = prmt(y, lane_base, 0x7614u);
+    const uint32_t a2 = prmt(y, lane_base, 0x7624u);
+    const uint32_t a3 = prmt(y, lane_base, 0x7634u);
+    // byte0 -> table 3, byte1 -> table 2, byte2 -> table 1, byte3 -> table 0
+    const uint32_t t3 = lds32_off<65536 + 128>(a0);
+    const uint32_t t2 = lds32_off<65536>(a1);
+    const uint32_t t1 = lds32_off<128>(a2);
+    const uint32_t t0 = lds32_off<0>(a3);
+    return t3 ^ t2 ^ t1 ^ t0;
+  };
+  auto fold = [&](uint32_t u) -> uint32_t {
+    const uint32_t* f = fold_s;
+    (void)f;
+    const uint32_t b0 = (u & 0xffu), b1 = (u >> 8) & 0xffu, b2 = (u >> 16) & 0xffu, b3 = u >> 24;
+    return lds32(fold_lane + (0 * 256 + b0) * (kBsFoldCopies * 4)) ^ lds32(fold_lane + (1 * 256 + b1) * (kBsFoldCopies * 4)) ^
+           lds32(fold_lane + (2 * 256 + b2) * (kBsFoldCopies * 4)) ^ lds32(fold_lane + (3 * 256 + b3) * (kBsFoldCopies * 4));
+  };
+
+  uint32_t crc_u[K + M];
+#pragma unroll
+  for (int i = 0; i < K + M; i++) crc_u[i] = 0;
+
+  const uint32_t n_items = p.n_stripes * p.n_seg;
+  const size_t seg_bytes = (size_t)p.tiles_per_seg * kBsTile;
+
+  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t s = item / p.n_seg, seg = item - s * p.n_seg;
+    uint8_t* sbase = p.base + (size_t)s * p.stripe_pitch;
+    const uint32_t T = (seg == p.n_seg - 1) ? p.tiles_last : p.tiles_per_seg;
+    const size_t seg_start = (size_t)seg * seg_bytes;
+
+    // one 32-byte group of every shard.  FULL = the whole tile lies inside [0, shard_len): no
+    // predicates, no tail masks (every tile but the last of a shard).
+    auto group = [&](auto full_tag, const size_t col) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const bool live = FULL || col < p.shard_len;
+      const int tail = (!FULL && live && col + 32 > p.shard_len) ? (int)(p.shard_len - col) : 0;
+      uint32_t msk[8];
+      if (!FULL) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int rem = tail - 4 * i;
+          msk[i] = (tail == 0 || rem >= 4) ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
+        }
+      }
+      uint32_t acc[8 * M];
+#pragma unroll
+      for (int i = 0; i < 8 * M; i++) acc[i] = 0;
+      uint32_t bufA[8], bufB[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) bufA[i] = bufB[i] = 0;
+      const uint8_t* src = sbase + col;
+      if (live) ldg256(src, bufA);
+      auto shard = [&](const int c, uint32_t (&w)[8]) {
+        if (!FULL) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) w[i] &= msk[i];
+        }
+        if (CRC) {
+          uint32_t u = crc_u[c];
+#pragma unroll
+          for (int i = 0; i < 8; i++) u = slice4(u ^ w[i]);
+          crc_u[c] = u;
+        }
+        bit_transpose8(w);
+        ApplyAt<Net, 0, K>::run(c, w, acc);   // c is a compile-time constant after unrolling
+      };
+#pragma unroll
+      for (int c = 0; c < K; c += 2) {
+        if (c + 1 < K && live) ldg256(src + (size_t)(c + 1) * p.shard_pitch, bufB);
+        shard(c, bufA);
+        if (c + 1 < K) {
+          if (c + 2 < K && live) ldg256(src + (size_t)(c + 2) * p.shard_pitch, bufA);
+          shard(c + 1, bufB);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < M; r++) {
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = acc[r * 8 + i];
+        bit_transpose8(o);
+        if (live) stg256(sbase + (size_t)(K + r) * p.shard_pitch + col, o);
+        if (CRC) {
+          uint32_t u = crc_u[K + r];
+#pragma unroll
+          for (int i = 0; i < 8; i++) u = slice4(u ^ o[i]);
+          crc_u[K + r] = u;
+        }
+      }
+    };
+
+    for (uint32_t t = 0; t < T; t++) {
+      if (CRC) {
+        // Horner step: skip the gap between the end of this thread's previous piece and this one
+#pragma unroll
+        for (int i = 0; i < K + M; i++) crc_u[i] = fold(crc_u[i]);
+      }
+      const size_t tile_start = seg_start + (size_t)t * kBsTile;
+      const size_t col0 = tile_start + (size_t)tid * kBsPiece;
+      if (tile_start + kBsTile <= p.shard_len) {
+#pragma unroll 1
+        for (int g = 0; g < kBsGroups; g++) group(std::true_type{}, col0 + (size_t)g * 32);
+      } else {
+#pragma unroll 1
+        for (int g = 0; g < kBsGroups; g++) group(std::false_type{}, col0 + (size_t)g * 32);
+      }
+    }
+
+    if (CRC && p.crc_part) {
+      const uint32_t kt = kth_s[tid];
+#pragma unroll
+      for (int q = 0; q < K + M; q++) {
+        uint32_t u = gf32_mul_dev(crc_u[q], kt, p.poly);
+        crc_u[q] = 0;
+        u = __reduce_xor_sync(0xffffffffu, u);
+        if (lane == 0) red_s[q * NW + warp] = u;
+      }
+      __syncthreads();
+      if (tid < K + M) {
+        uint32_t u = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; w2++) u ^= red_s[tid * NW + w2];
+        p.crc_part[((size_t)s * p.n_slots + tid) * p.n_seg + seg] = u;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side dispatch
+// ------------------------------------------------------------------------------------------
+template <int K, int M>
+static bool rows_match(const uint8_t* rows) {
+  for (int i = 0; i < K * M; i++)
+    if (rows[i] != BsNet<K, M>::kRows[i]) return false;
+  return true;
+}
+
+template <int K, int M>
+static cudaError_t launch_cfg(const BsParams& p, bool crc, int grid, cudaStream_t st) {
+  static bool configured = false;   // per process; attribute is per device function, set for every device lazily
+  cudaError_t e;
+  (void)configured;
+  if ((e = cudaFuncSetAttribute(rs_bs_kernel<K, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)kBsSmemBytes)) != cudaSuccess)
+    return e;
+  if (crc) rs_bs_kernel<K, M, true><<<grid, kBsThreads, kBsSmemBytes, st>>>(p);
+  else rs_bs_kernel<K, M, false><<<grid, kBsThreads, 4096, st>>>(p);
+  return cudaGetLastError();
+}
+
+#define CUBEEC_BS_CONFIGS(X) X(4, 2) X(6, 3) X(12, 4) X(20, 4) X(16, 4) X(10, 4) X(3, 3) X(4, 4) X(8, 4) X(6, 2) X(10, 2) X(5, 2)
+
+bool bs_supported(int k, int m, const uint8_t* parity_rows) {
+#define X(KK, MM) \
+  if (k == KK && m == MM) return rows_match<KK, MM>(parity_rows);
+  CUBEEC_BS_CONFIGS(X)
+#undef X
+  return false;
+}
+
+cudaError_t launch_bs(int k, int m, const BsParams& p, bool crc, int grid, cudaStream_t st) {
+#define X(KK, MM) \
+  if (k == KK && m == MM) return launch_cfg<KK, MM>(p, crc, grid, st);
+  CUBEEC_BS_CONFIGS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace cbe

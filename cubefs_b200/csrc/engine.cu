@@ -60,6 +60,7 @@ extern "C" const char* cubeec_strerror(int code) {
 extern "C" const char* cubeec_last_error(void) { return t_last_error.c_str(); }
 extern "C" uint64_t cubeec_kernel_launches(void) { return g_launches.load(); }
 extern "C" const char* cubeec_last_kernel(void) { return t_last_kernel; }
+extern "C" void cubeec_debug_force_kernel(int which);
 
 // ------------------------------------------------------------------------------------------
 // per-device context
@@ -85,6 +86,10 @@ struct DevCtx {
   size_t smem_limit = 0;
   GfDeviceTables* d_gf = nullptr;
   CrcDeviceTables* d_crc[2] = {nullptr, nullptr};
+  // bit-sliced kernel: lane-private slicing-table image, Horner (fold) tables, per-thread alignment constants
+  uint32_t* d_bs_slice[2] = {nullptr, nullptr};
+  uint32_t* d_bs_fold[2] = {nullptr, nullptr};
+  uint32_t* d_bs_kthread[2] = {nullptr, nullptr};
   std::mutex mu;
   std::condition_variable cv;
   std::vector<Lane*> free_lanes;
@@ -100,7 +105,7 @@ struct Global {
   int init_rc = CUBEEC_OK;
   std::vector<int> devices;
   std::vector<std::unique_ptr<DevCtx>> ctx;
-  CrcPoly poly[2] = {{0xEDB88320u}, {0x82F63B78u}};
+  CrcPoly poly[2] = {{0xEDB88320u, 0xFFFFFFFFLL}, {0x82F63B78u, 0x7FFFFFFFLL}};
 };
 Global g;
 
@@ -121,8 +126,28 @@ int setup_device(DevCtx& c) {
     for (int t = 0; t < 1024; t++)
       ct->kthread[t] = t < kTabThreads ? P.shift_bytes_const((int64_t)kTabTile - 16 * (t + 1)) : 0;
     ct->poly = P.poly;
+    ct->ord = (uint32_t)P.ord;
+    if (P.xpow_raw((uint64_t)P.ord) != 0x80000000u || P.mul(P.xpow(-12345), P.xpow(12345)) != 0x80000000u) {
+      t_last_error = "CRC polynomial order self-check failed";
+      return CUBEEC_ERR_CUDA;
+    }
     CU(cudaMalloc(&c.d_crc[pi], sizeof(CrcDeviceTables)));
     CU(cudaMemcpy(c.d_crc[pi], ct.get(), sizeof(CrcDeviceTables), cudaMemcpyHostToDevice));
+    // bitslice.cu tables: image offset (j>>1)*65536 + v*256 + (j&1)*128 + lane*4 = slice[j][v]
+    std::vector<uint32_t> img(kBsSliceImageBytes / 4);
+    for (int j = 0; j < 4; j++)
+      for (int v = 0; v < 256; v++)
+        for (int l = 0; l < 32; l++) img[((size_t)(j >> 1) * 65536 + (size_t)v * 256 + (size_t)(j & 1) * 128) / 4 + l] = ct->slice[j][v];
+    uint32_t fold[4][256];
+    crc_const_mul_tables(P, P.shift_bytes_const((int64_t)kBsTile - kBsPiece), fold);
+    std::vector<uint32_t> kth(kBsThreads);
+    for (int t = 0; t < kBsThreads; t++) kth[t] = P.shift_bytes_const((int64_t)kBsTile - (int64_t)kBsPiece * (t + 1));
+    CU(cudaMalloc(&c.d_bs_slice[pi], kBsSliceImageBytes));
+    CU(cudaMemcpy(c.d_bs_slice[pi], img.data(), kBsSliceImageBytes, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c.d_bs_fold[pi], sizeof(fold)));
+    CU(cudaMemcpy(c.d_bs_fold[pi], fold, sizeof(fold), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c.d_bs_kthread[pi], kth.size() * 4));
+    CU(cudaMemcpy(c.d_bs_kthread[pi], kth.data(), kth.size() * 4, cudaMemcpyHostToDevice));
   }
   return CUBEEC_OK;
 }
@@ -230,6 +255,19 @@ struct cubeec {
   std::vector<Pattern> verify_passes;
   std::vector<Pattern*> d_enc;      // per ctx: device copy [n_passes]
   std::vector<Pattern*> d_verify;   // same, crc_in = 0
+  bool bs_ok = false;               // a specialised bit-sliced network exists for this matrix
+  // Batched-reconstruct plans: the pattern tables of a whole presence array, resident on a device,
+  // so that repeating a repair batch costs no host-side matrix work or uploads.
+  struct Plan {
+    int device = 0;
+    bool data_only = false;
+    std::vector<uint8_t> present;
+    Pattern* d_pat = nullptr;
+    uint32_t* d_pos = nullptr;
+    size_t n_pass = 0, n_pat = 0;
+    std::vector<int> nin;
+  };
+  std::vector<std::unique_ptr<Plan>> plans;
   std::mutex mu;
   // decode pattern cache: presence string (+data_only) -> passes
   std::map<std::string, std::vector<Pattern>> dec_cache;
@@ -305,14 +343,17 @@ int decode_passes(cubeec* h, const uint8_t* present, bool data_only, std::vector
 struct Geometry {
   uint32_t n_seg, tiles_per_seg, tiles_last;
   int grid;
+  uint32_t tile;   // bytes of a shard per tile
 };
 
-Geometry pick_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes, bool per_stripe_patterns) {
+Geometry pick_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes, bool per_stripe_patterns,
+                       uint32_t tile = kTabTile) {
   Geometry gm;
-  const uint64_t tiles_total = (shard_len + kTabTile - 1) / kTabTile;
+  gm.tile = tile;
+  const uint64_t tiles_total = (shard_len + tile - 1) / tile;
   uint64_t want_items = (uint64_t)c.sm_count * (per_stripe_patterns ? 2 : 8);
   uint64_t n_seg = (want_items + n_stripes - 1) / std::max<size_t>(n_stripes, 1);
-  const uint64_t max_seg = std::max<uint64_t>(1, tiles_total / 4);
+  const uint64_t max_seg = std::max<uint64_t>(1, tiles_total / (tile >= 32768 ? 1 : 4));
   n_seg = std::max<uint64_t>(1, std::min(n_seg, max_seg));
   uint64_t tps = (tiles_total + n_seg - 1) / n_seg;
   n_seg = (tiles_total + tps - 1) / tps;
@@ -372,8 +413,8 @@ int finalize_crc(DevCtx& c, cudaStream_t stream, const uint32_t* d_crc_part, siz
   f.n_units = (uint32_t)(n_stripes * n_slots);
   f.n_slots = (uint32_t)n_slots;
   f.n_seg = gm.n_seg;
-  const int64_t seg_bytes = (int64_t)gm.tiles_per_seg * kTabTile;
-  const int64_t last_bytes = (int64_t)gm.tiles_last * kTabTile;
+  const int64_t seg_bytes = (int64_t)gm.tiles_per_seg * gm.tile;
+  const int64_t last_bytes = (int64_t)gm.tiles_last * gm.tile;
   const int64_t virt = (int64_t)(gm.n_seg - 1) * seg_bytes + last_bytes;
   f.x_full = P.shift_bytes_const(seg_bytes);
   f.x_last = P.shift_bytes_const(last_bytes);
@@ -422,9 +463,18 @@ size_t ctx_index(const DevCtx* c) {
 
 // Bytes of CRC scratch (per-segment remainders) an encode of this geometry needs.
 size_t crc_part_bytes(const DevCtx& c, size_t shard_len, size_t n_stripes, int n_slots) {
-  const Geometry gm = pick_geometry(c, shard_len, n_stripes, false);
-  return n_stripes * (size_t)n_slots * gm.n_seg * sizeof(uint32_t);
+  // upper bound over both kernels' geometries
+  const Geometry g1 = pick_geometry(c, shard_len, n_stripes, false);
+  const Geometry g2 = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
+  return n_stripes * (size_t)n_slots * std::max(g1.n_seg, g2.n_seg) * sizeof(uint32_t);
 }
+
+// The bit-sliced kernel needs 32-byte columns: base and pitches 32-aligned, room for whole groups.
+bool bs_layout_ok(const uint8_t* d_base, size_t shard_len, size_t shard_pitch, size_t stripe_pitch) {
+  return (((uintptr_t)d_base | shard_pitch | stripe_pitch) & 31) == 0 && shard_pitch >= round_up(shard_len, 32);
+}
+
+std::atomic<int> g_force_kernel{0};   // 0 auto, 1 table kernel only (tests / A-B measurements)
 
 // Encode (mode 0) or verify (mode 1) a device-resident batch.  d_part: caller scratch of
 // crc_part_bytes() when CRCs are wanted, or nullptr to use the stream-ordered allocator.
@@ -434,8 +484,43 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
   if (h->m == 0 && !d_crc_out) return CUBEEC_OK;
   const int n = h->k + h->m;
   const size_t ci = ctx_index(&c);
-  const Geometry gm = pick_geometry(c, shard_len, n_stripes, false);
   const bool want_crc = mode == 0 && d_crc_out;
+  if (mode == 0 && h->bs_ok && g_force_kernel.load() != 1 && bs_layout_ok(d_base, shard_len, shard_pitch, stripe_pitch)) {
+    // hot path: bit-sliced XOR-network kernel (bitslice.cu)
+    const Geometry gm = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
+    bool own = false;
+    if (want_crc && !d_part) {
+      CU(cudaMallocAsync(&d_part, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
+      own = true;
+    }
+    BsParams bp;
+    std::memset(&bp, 0, sizeof(bp));
+    bp.base = d_base;
+    bp.stripe_pitch = stripe_pitch;
+    bp.shard_pitch = shard_pitch;
+    bp.shard_len = (uint32_t)shard_len;
+    bp.n_stripes = (uint32_t)n_stripes;
+    bp.n_seg = gm.n_seg;
+    bp.tiles_per_seg = gm.tiles_per_seg;
+    bp.tiles_last = gm.tiles_last;
+    bp.n_slots = (uint32_t)n;
+    bp.crc_part = want_crc ? d_part : nullptr;
+    const int pi = crc_poly ? 1 : 0;
+    bp.slice_image = c.d_bs_slice[pi];
+    bp.fold_tables = c.d_bs_fold[pi];
+    bp.kthread = c.d_bs_kthread[pi];
+    bp.poly = g.poly[pi].poly;
+    CU(launch_bs(h->k, h->m, bp, want_crc, gm.grid, stream));
+    g_launches++;
+    t_last_kernel = want_crc ? "rs_bs_kernel<crc>" : "rs_bs_kernel";
+    if (want_crc) {
+      int rc = finalize_crc(c, stream, d_part, n_stripes, n, shard_len, gm, crc_poly, nullptr, d_crc_out);
+      if (rc) return rc;
+      if (own) CU(cudaFreeAsync(d_part, stream));
+    }
+    return CUBEEC_OK;
+  }
+  const Geometry gm = pick_geometry(c, shard_len, n_stripes, false);
   const auto& passes = want_crc ? h->enc_passes : h->verify_passes;
   const Pattern* dp = want_crc ? h->d_enc[ci] : h->d_verify[ci];
   std::vector<const Pattern*> pp;
@@ -462,6 +547,8 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
 }
 
 }  // namespace
+
+extern "C" void cubeec_debug_force_kernel(int which) { g_force_kernel.store(which); }
 
 // ------------------------------------------------------------------------------------------
 // process-wide API
@@ -535,6 +622,7 @@ extern "C" int cubeec_create(int k, int m, const uint8_t* parity_rows, cubeec_t*
     make_passes(ins, outs, rows, false, h->verify_passes);
     rc = upload_handle_patterns(h.get());
     if (rc) return rc;
+    h->bs_ok = bs_supported(k, m, rows.data());
   }
   *out = h.release();
   return CUBEEC_OK;
@@ -542,6 +630,11 @@ extern "C" int cubeec_create(int k, int m, const uint8_t* parity_rows, cubeec_t*
 
 extern "C" void cubeec_destroy(cubeec_t* h) {
   if (!h) return;
+  for (auto& pl : h->plans) {
+    cudaSetDevice(pl->device);
+    if (pl->d_pat) cudaFree(pl->d_pat);
+    if (pl->d_pos) cudaFree(pl->d_pos);
+  }
   for (size_t ci = 0; ci < h->d_enc.size() && ci < g.ctx.size(); ci++) {
     cudaSetDevice(g.ctx[ci]->device);
     if (h->d_enc[ci]) cudaFree(h->d_enc[ci]);
@@ -647,66 +740,93 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
   if (!c) return CUBEEC_ERR_INVALID_ARG;
   CU(cudaSetDevice(device));
   const int n = h->k + h->m;
-  // distinct presence patterns -> pattern ids
-  std::map<std::string, uint32_t> ids;
-  std::vector<std::vector<Pattern>> pat_passes;
-  std::vector<uint32_t> pos(n_stripes);
-  size_t n_pass = 0;
-  for (size_t s = 0; s < n_stripes; s++) {
-    std::string key((const char*)present + s * n, (size_t)n);
-    for (auto& ch : key) ch = ch ? 1 : 0;
-    auto it = ids.find(key);
-    if (it == ids.end()) {
-      std::vector<Pattern> passes;
-      rc = decode_passes(h, (const uint8_t*)key.data(), data_only != 0, passes);
-      if (rc) return rc;
-      n_pass = std::max(n_pass, passes.size());
-      it = ids.emplace(key, (uint32_t)pat_passes.size()).first;
-      pat_passes.push_back(std::move(passes));
-    }
-    pos[s] = it->second;
-  }
-  // drop passes that do nothing for every pattern
-  while (n_pass > 0) {
-    bool any = false;
-    for (auto& pp : pat_passes)
-      if (pp.size() >= n_pass && pp[n_pass - 1].n_out) any = true;
-    if (any) break;
-    n_pass--;
-  }
-  if (n_pass == 0) return CUBEEC_OK;
-  const size_t n_pat = pat_passes.size();
-  std::vector<Pattern> flat(n_pass * n_pat);
-  std::memset(flat.data(), 0, flat.size() * sizeof(Pattern));
-  std::vector<int> nin(n_pass, 0), ncrc(n_pass, 0);
-  for (size_t j = 0; j < n_pass; j++)
-    for (size_t q = 0; q < n_pat; q++)
-      if (j < pat_passes[q].size()) {
-        flat[j * n_pat + q] = pat_passes[q][j];
-        nin[j] = std::max<int>(nin[j], pat_passes[q][j].n_in);
+  // plan lookup (same presence array as an earlier call on this device?)
+  cubeec::Plan* plan = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    for (auto& pl : h->plans)
+      if (pl->device == device && pl->data_only == (data_only != 0) && pl->present.size() == n_stripes * (size_t)n &&
+          std::memcmp(pl->present.data(), present, pl->present.size()) == 0) {
+        plan = pl.get();
+        break;
       }
+  }
+  std::unique_ptr<cubeec::Plan> fresh;
+  if (!plan) {
+    // distinct presence patterns -> pattern ids
+    std::map<std::string, uint32_t> ids;
+    std::vector<std::vector<Pattern>> pat_passes;
+    std::vector<uint32_t> pos(n_stripes);
+    size_t n_pass = 0;
+    for (size_t s = 0; s < n_stripes; s++) {
+      std::string key((const char*)present + s * n, (size_t)n);
+      for (auto& ch : key) ch = ch ? 1 : 0;
+      auto it = ids.find(key);
+      if (it == ids.end()) {
+        std::vector<Pattern> passes;
+        rc = decode_passes(h, (const uint8_t*)key.data(), data_only != 0, passes);
+        if (rc) return rc;
+        n_pass = std::max(n_pass, passes.size());
+        it = ids.emplace(key, (uint32_t)pat_passes.size()).first;
+        pat_passes.push_back(std::move(passes));
+      }
+      pos[s] = it->second;
+    }
+    // drop passes that do nothing for every pattern
+    while (n_pass > 0) {
+      bool any = false;
+      for (auto& pp : pat_passes)
+        if (pp.size() >= n_pass && pp[n_pass - 1].n_out) any = true;
+      if (any) break;
+      n_pass--;
+    }
+    if (n_pass == 0) return CUBEEC_OK;
+    const size_t n_pat = pat_passes.size();
+    std::vector<Pattern> flat(n_pass * n_pat);
+    std::memset(flat.data(), 0, flat.size() * sizeof(Pattern));
+    fresh = std::make_unique<cubeec::Plan>();
+    fresh->device = device;
+    fresh->data_only = data_only != 0;
+    fresh->present.assign(present, present + n_stripes * (size_t)n);
+    fresh->n_pass = n_pass;
+    fresh->n_pat = n_pat;
+    fresh->nin.assign(n_pass, 0);
+    for (size_t j = 0; j < n_pass; j++)
+      for (size_t q = 0; q < n_pat; q++)
+        if (j < pat_passes[q].size()) {
+          flat[j * n_pat + q] = pat_passes[q][j];
+          fresh->nin[j] = std::max<int>(fresh->nin[j], pat_passes[q][j].n_in);
+        }
+    CU(cudaMalloc(&fresh->d_pat, flat.size() * sizeof(Pattern)));
+    CU(cudaMalloc(&fresh->d_pos, n_stripes * sizeof(uint32_t)));
+    CU(cudaMemcpy(fresh->d_pat, flat.data(), flat.size() * sizeof(Pattern), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(fresh->d_pos, pos.data(), n_stripes * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    plan = fresh.get();
+  }
   LaneLease lease;
   cudaStream_t st = (cudaStream_t)stream;
   if (!st) {
     if ((rc = lease.acquire(c))) return rc;
     st = lease.lane->stream;
   }
-  Pattern* d_pat = nullptr;
-  uint32_t* d_pos = nullptr;
-  CU(cudaMallocAsync(&d_pat, flat.size() * sizeof(Pattern), st));
-  CU(cudaMallocAsync(&d_pos, n_stripes * sizeof(uint32_t), st));
-  CU(cudaMemcpyAsync(d_pat, flat.data(), flat.size() * sizeof(Pattern), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_pos, pos.data(), n_stripes * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   std::vector<const Pattern*> pp;
-  for (size_t j = 0; j < n_pass; j++) pp.push_back(d_pat + j * n_pat);
-  const Geometry gm = pick_geometry(*c, shard_len, n_stripes, n_pat > 1);
-  rc = run_passes(*c, st, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, n, pp, nin, ncrc, d_pos,
-                  0, nullptr, nullptr, 0, gm);
+  for (size_t j = 0; j < plan->n_pass; j++) pp.push_back(plan->d_pat + j * plan->n_pat);
+  std::vector<int> ncrc(plan->n_pass, 0);
+  const Geometry gm = pick_geometry(*c, shard_len, n_stripes, plan->n_pat > 1);
+  rc = run_passes(*c, st, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, n, pp, plan->nin, ncrc,
+                  plan->d_pos, 0, nullptr, nullptr, 0, gm);
   if (rc) return rc;
-  CU(cudaFreeAsync(d_pat, st));
-  CU(cudaFreeAsync(d_pos, st));
-  // the host staging vectors (flat, pos) are pageable: the async copies above were staged by the
-  // runtime before returning, so they may go out of scope here.
+  if (fresh) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->plans.size() < 16) {
+      h->plans.push_back(std::move(fresh));
+    } else {
+      // cache full: this plan is single-use; release it once the stream has consumed it
+      CU(cudaStreamSynchronize(st));
+      cudaFree(fresh->d_pat);
+      cudaFree(fresh->d_pos);
+    }
+  }
   if (!stream) CU(cudaStreamSynchronize(st));
   return CUBEEC_OK;
 }

@@ -94,6 +94,9 @@ inline bool build_generator(int k, int total, std::vector<uint8_t>& out) {
 // ---------------------------------------------------------------------------------------
 struct CrcPoly {
   uint32_t poly;  // 0xEDB88320 (IEEE, what BlobStore uses) or 0x82F63B78 (Castagnoli)
+  // multiplicative order of x modulo the polynomial: 2^32-1 for IEEE (primitive); the Castagnoli
+  // polynomial is (x+1) * (primitive of degree 31), so x has order 2^31-1 there.
+  int64_t ord;
   // a(x) * b(x) mod P
   uint32_t mul(uint32_t a, uint32_t b) const {
     uint32_t r = 0;
@@ -104,12 +107,14 @@ struct CrcPoly {
     }
     return r;
   }
-  // x^n mod P, n may be any integer (negative exponents via the group order 2^32-1;
-  // both polynomials are primitive, so x has that order).
+  // x^n mod P, n may be any integer (negative exponents via the order of x).
   uint32_t xpow(int64_t n) const {
-    const int64_t ord = 0xFFFFFFFFLL;
     n %= ord;
     if (n < 0) n += ord;
+    return xpow_raw((uint64_t)n);
+  }
+  // x^n mod P for n >= 0 with no use of the order (self-check of `ord`)
+  uint32_t xpow_raw(uint64_t n) const {
     uint32_t result = 0x80000000u;  // x^0
     uint32_t base = 0x40000000u;    // x^1
     while (n) {

@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(kTabThreads) crc_range_kernel(const CrcRangePa
       for (int w = 0; w < NW; w++) r ^= red[w];
       // virtual end = a_al + T*TILE; remove the z zero bytes behind the real end e
       const uint64_t z = (uint64_t)a_al + (uint64_t)T * kTabTile - e;
-      const uint64_t ord = 0xFFFFFFFFull;
+      const uint64_t ord = p.crc->ord;
       const uint64_t neg = (ord - (8 * z) % ord) % ord;
       r = gf32_mul(r, gf32_xpow(neg, poly), poly);
       const uint32_t init_term = gf32_mul(0xFFFFFFFFu, gf32_xpow(8ull * (e - a), poly), poly);

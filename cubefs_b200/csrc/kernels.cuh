@@ -37,7 +37,8 @@ struct alignas(16) CrcDeviceTables {
   uint32_t shift_tile[4][256]; // register * x^(8*tile bytes): Horner step between a thread's pieces
   uint32_t kthread[1024];      // x^(8*(tile - 16*(tid+1))): aligns a thread's partial to the tile end
   uint32_t poly;
-  uint32_t pad[3];
+  uint32_t ord;                // multiplicative order of x mod poly (for negative shifts)
+  uint32_t pad[2];
 };
 
 struct TabParams {
@@ -98,5 +99,36 @@ cudaError_t launch_crc_ranges(const CrcRangeParams& p, int grid, cudaStream_t st
 cudaError_t launch_crc_combine(const uint32_t* unit_crc, uint32_t n_buffers, uint32_t units_per_buffer,
                                uint32_t len, uint32_t block, uint32_t poly, uint32_t* whole,
                                cudaStream_t stream);
+
+// ---- bit-sliced encode kernel (bitslice.cu) ----------------------------------------------
+// Shared-memory image of the lane-private slicing tables (R = 32 copies):
+//   table j, byte v, lane l  ->  byte offset (j>>1)*65536 + v*256 + (j&1)*128 + l*4
+// placed at a 64 KiB aligned shared address so that one PRMT builds the whole LDS address:
+//   addr = (hi16 of table base) | v << 8 | lane*4      (+ immediate for the table number)
+constexpr int kBsThreads = 512;
+constexpr int kBsGroups = 2;                                  // 32-byte groups per thread per tile
+constexpr int kBsPiece = 32 * kBsGroups;                      // contiguous bytes per thread per tile
+constexpr int kBsTile = kBsThreads * kBsPiece;                // bytes of every shard per tile
+constexpr int kBsFoldCopies = 4;
+constexpr size_t kBsSliceImageBytes = 2 * 65536;
+constexpr size_t kBsMiscBytes = 4 * 256 * kBsFoldCopies * 4 + kBsThreads * 4 + 64;
+constexpr size_t kBsSmemBytes = 65536 + kBsSliceImageBytes + 1024;
+
+struct BsParams {
+  uint8_t* base;
+  size_t stripe_pitch, shard_pitch;
+  uint32_t shard_len, n_stripes;
+  uint32_t n_seg, tiles_per_seg, tiles_last;
+  uint32_t n_slots;
+  uint32_t* crc_part;                 // [n_stripes][n_slots][n_seg] or nullptr
+  const uint32_t* slice_image;        // global: 128 KiB replicated slicing tables (kBsSliceImageBytes)
+  const uint32_t* fold_tables;        // global: [4][256] register * x^(8*(tile - piece))
+  const uint32_t* kthread;            // global: [kBsThreads] x^(8*(tile - piece*(tid+1)))
+  uint32_t poly;
+};
+
+
+bool bs_supported(int k, int m, const uint8_t* parity_rows);   // a specialised network exists for this matrix
+cudaError_t launch_bs(int k, int m, const BsParams& p, bool crc, int grid, cudaStream_t st);
 
 }  // namespace cbe

@@ -71,6 +71,8 @@ def load() -> C.CDLL:
     L.cubeec_dev_crc32.argtypes = [C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp, vp]
     L.cubeec_kernel_launches.restype = C.c_uint64
     L.cubeec_last_kernel.restype = C.c_char_p
+    L.cubeec_debug_force_kernel.argtypes = [C.c_int]
+    L.cubeec_debug_force_kernel.restype = None
     _lib = L
     return L
 
@@ -99,6 +101,11 @@ def kernel_launches() -> int:
 
 def last_kernel() -> str:
     return load().cubeec_last_kernel().decode()
+
+
+def force_kernel(which: int) -> None:
+    """Measurement aid: 0 = automatic choice, 1 = generic table kernel only."""
+    load().cubeec_debug_force_kernel(which)
 
 
 class StripeDesc(C.Structure):

@@ -309,3 +309,47 @@ def test_linearity_and_roundtrip_at_scale(cb):
     eng.dev_reconstruct(c.data_ptr(), S, P, n * P, ns, present)
     torch.cuda.synchronize()
     assert torch.equal(c[:, :, :S], good[:, :, :S])
+
+
+def test_kernel_selection_and_ab_equivalence(cb, oracle):
+    """The bit-sliced kernel serves the specialised matrices on 32-byte-aligned layouts; the generic
+    table kernel must produce the same bytes and CRCs (A/B through cubeec_debug_force_kernel)."""
+    import torch
+    for (k, m, S) in ((12, 4, 349526), (4, 2, 65536), (6, 3, 4096 + 7), (20, 4, 70001), (10, 4, 33)):
+        n, P, ns = k + m, (S + 127) // 128 * 128, 5
+        rng = np.random.default_rng(k * 7 + m)
+        host = rng.integers(0, 256, (ns, n, P), dtype=np.uint8)
+        eng = cb.RSEngine(k, m)
+        outs = []
+        for force, want in ((0, "rs_bs_kernel<crc>"), (1, "rs_tab_kernel<crc>")):
+            cb.force_kernel(force)
+            try:
+                dev = torch.from_numpy(host).cuda()
+                dcrc = torch.zeros(ns * n, dtype=torch.int32, device="cuda")
+                eng.dev_encode(dev.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr())
+                assert cb.last_kernel() == want
+                torch.cuda.synchronize()
+                outs.append((dev.cpu().numpy(), dcrc.cpu().numpy().view(np.uint32).reshape(ns, n)))
+            finally:
+                cb.force_kernel(0)
+        assert (outs[0][0][:, :, :S] == outs[1][0][:, :, :S]).all()
+        assert (outs[0][1] == outs[1][1]).all()
+        ora = oracle.RS(k, m)
+        for s in range(ns):
+            sh = [host[s, i, :S].copy() for i in range(n)]
+            ora.encode(sh)
+            for i in range(n):
+                assert (outs[0][0][s, i, :S] == sh[i]).all(), (k, m, s, i)
+                assert outs[0][1][s, i] == zlib.crc32(sh[i].tobytes()), (k, m, s, i)
+        # a 16-byte-aligned (not 32) layout must still work, through the table kernel
+        dev = torch.from_numpy(host).cuda()
+        flat = torch.zeros(dev.numel() + 64, dtype=torch.uint8, device="cuda")
+        off = 16 - (flat.data_ptr() % 32) if flat.data_ptr() % 32 != 16 else 0
+        view = flat[off:off + dev.numel()]
+        assert view.data_ptr() % 32 == 16
+        view.copy_(dev.reshape(-1))
+        eng.dev_encode(view.data_ptr(), S, P, n * P, ns)
+        assert cb.last_kernel() == "rs_tab_kernel"
+        torch.cuda.synchronize()
+        got = view.cpu().numpy().reshape(ns, n, P)
+        assert (got[:, :, :S] == outs[0][0][:, :, :S]).all()
