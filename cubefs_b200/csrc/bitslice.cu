@@ -62,6 +62,8 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b) {
   asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "n"(MASK));
   return d;
 }
+// (Measured: moving the right shifts or the byte-0 address to IMAD.HI on the FMA pipe does not
+// pay -- IMAD.HI issues at a quarter of the IMAD rate and lengthens the serial CRC chain.)
 template <int S, uint32_t MASK>
 __device__ __forceinline__ void delta_swap(uint32_t& a, uint32_t& b) {
   const uint32_t na = bitsel<MASK>(a, b * (1u << S));
@@ -168,7 +170,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
 
   // one slicing-by-4 step: register after absorbing the 4 bytes of y (= state ^ data word)
   auto slice4 = [&](uint32_t y) -> uint32_t {
-    const uint32_t a0 = prmt(y, lane_base, 0x7604u);   // (table hi) | byte0 << 8 | lane*4
+    // lookup address = (table hi) | byte << 8 | lane*4: one PRMT per byte
+    const uint32_t a0 = prmt(y, lane_base, 0x7604u);
     const uint32_t a1 = prmt(y, lane_base, 0x7614u);
     const uint32_t a2 = prmt(y, lane_base, 0x7624u);
     const uint32_t a3 = prmt(y, lane_base, 0x7634u);
@@ -217,11 +220,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
       uint32_t acc[8 * M];
 #pragma unroll
       for (int i = 0; i < 8 * M; i++) acc[i] = 0;
-      uint32_t bufA[8], bufB[8];
+      uint32_t bufA[8], bufB[8], bufC[8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) bufA[i] = bufB[i] = 0;
+      for (int i = 0; i < 8; i++) bufA[i] = bufB[i] = bufC[i] = 0;
       const uint8_t* src = sbase + col;
-      if (live) ldg256(src, bufA);
       auto shard = [&](const int c, uint32_t (&w)[8]) {
         if (!FULL) {
 #pragma unroll
@@ -236,13 +238,37 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
         bit_transpose8(w);
         ApplyAt<Net, 0, K>::run(c, w, acc);   // c is a compile-time constant after unrolling
       };
+      auto fetch = [&](const int c, uint32_t (&w)[8]) {
+        if (c < K && live) ldg256(src + (size_t)c * p.shard_pitch, w);
+      };
+      if (CRC) {
+        // ALU/issue bound: one shard of look-ahead is enough and registers are at the limit
+        fetch(0, bufA);
 #pragma unroll
-      for (int c = 0; c < K; c += 2) {
-        if (c + 1 < K && live) ldg256(src + (size_t)(c + 1) * p.shard_pitch, bufB);
-        shard(c, bufA);
-        if (c + 1 < K) {
-          if (c + 2 < K && live) ldg256(src + (size_t)(c + 2) * p.shard_pitch, bufA);
-          shard(c + 1, bufB);
+        for (int c = 0; c < K; c += 2) {
+          fetch(c + 1, bufB);
+          shard(c, bufA);
+          if (c + 1 < K) {
+            fetch(c + 2, bufA);
+            shard(c + 1, bufB);
+          }
+        }
+      } else {
+        // latency bound: keep two shards (64 B per thread) in flight ahead of the one being coded
+        fetch(0, bufA);
+        fetch(1, bufB);
+#pragma unroll
+        for (int c = 0; c < K; c += 3) {
+          fetch(c + 2, bufC);
+          shard(c, bufA);
+          if (c + 1 < K) {
+            fetch(c + 3, bufA);
+            shard(c + 1, bufB);
+          }
+          if (c + 2 < K) {
+            fetch(c + 4, bufB);
+            shard(c + 2, bufC);
+          }
         }
       }
 #pragma unroll

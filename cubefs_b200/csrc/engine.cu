@@ -351,7 +351,10 @@ Geometry pick_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes, bool
   Geometry gm;
   gm.tile = tile;
   const uint64_t tiles_total = (shard_len + tile - 1) / tile;
+  // enough work items to balance the persistent CTAs; whole stripes once the batch is large
+  // (per-item costs: table rebuild for per-stripe patterns, CRC alignment multiply)
   uint64_t want_items = (uint64_t)c.sm_count * (per_stripe_patterns ? 2 : 8);
+  if (n_stripes >= (uint64_t)c.sm_count * 4) want_items = n_stripes;
   uint64_t n_seg = (want_items + n_stripes - 1) / std::max<size_t>(n_stripes, 1);
   const uint64_t max_seg = std::max<uint64_t>(1, tiles_total / (tile >= 32768 ? 1 : 4));
   n_seg = std::max<uint64_t>(1, std::min(n_seg, max_seg));
@@ -510,6 +513,7 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
     bp.fold_tables = c.d_bs_fold[pi];
     bp.kthread = c.d_bs_kthread[pi];
     bp.poly = g.poly[pi].poly;
+    bp.k65536 = 65536u;
     CU(launch_bs(h->k, h->m, bp, want_crc, gm.grid, stream));
     g_launches++;
     t_last_kernel = want_crc ? "rs_bs_kernel<crc>" : "rs_bs_kernel";

@@ -56,6 +56,25 @@ __device__ __forceinline__ void stg_stream(void* p, uint4 v) {
                : "memory");
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// byte B of w, zero-extended (one PRMT)
+template <int B>
+__device__ __forceinline__ uint32_t byte_of(uint32_t w) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(w), "n"(0x4440 + B));
+  return d;
+}
+// table lookup address: v * 256 + base  (multiply-add on the FMA pipe)
+__device__ __forceinline__ uint32_t row_addr(uint32_t v, uint32_t base) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(d) : "r"(v), "r"(base));
+  return d;
+}
+
 // zero the bytes at positions >= n (0 < n < 16) of a 16-byte piece
 __device__ __forceinline__ uint4 keep_head(uint4 d, int n) {
   uint32_t w[4] = {d.x, d.y, d.z, d.w};
@@ -131,7 +150,10 @@ __device__ __forceinline__ uint32_t crc_constmul(uint32_t u, const uint32_t* __r
 //   * optionally advances a per-shard CRC register: piece remainder by slicing-by-4, Horner
 //     step (multiply by x^(8*TILE)) between pieces, so bytes are checksummed while in registers.
 // Tables are replicated R times (copy = lane % R) to cut bank conflicts; R is the largest
-// power of two <= 16 that fits next to the CRC state in shared memory.
+// power of two <= 16 that fits next to the CRC state in shared memory.  Layout: one 256-byte row
+// per byte value v holding 64/R shards x R copies, 64 KiB per group of 64/R shards, so a lookup
+// address is  v*256 + (per-shard, per-lane base): one PRMT (byte extract, ALU pipe), one
+// multiply-add (FMA pipe), one LDS.
 // ------------------------------------------------------------------------------------------
 template <int R, bool CRC>
 __global__ void __launch_bounds__(kTabThreads, 1) rs_tab_kernel(const TabParams p, const int n_crc_slots) {
@@ -160,7 +182,9 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tab_kernel(const TabParams 
     off += (size_t)n_crc_slots * NW * 4;
     off = (off + 127) & ~(size_t)127;
   }
-  uint32_t* tab = reinterpret_cast<uint32_t*>(smem + off);   // [n_in][256][R]
+  constexpr int SPR = 64 / R;                                 // shards per 256-byte table row
+  uint8_t* tab = smem + off;                                   // [ceil(n_in/SPR)][256 rows][SPR][R] u32
+  const uint32_t tab_s = smem_u32(tab);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -206,8 +230,9 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tab_kernel(const TabParams 
             if (co) e |= (uint32_t)gf_s->exp[gf_s->log[co] + lv] << (8 * r);
           }
         }
+        uint32_t* row = reinterpret_cast<uint32_t*>(tab + (size_t)(c / SPR) * 65536 + (size_t)v * 256 + (size_t)(c % SPR) * (4 * R));
 #pragma unroll
-        for (int q = 0; q < R; q++) tab[(size_t)idx * R + q] = e;
+        for (int q = 0; q < R; q++) row[q] = e;
       }
       __syncthreads();
     }
@@ -226,33 +251,43 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tab_kernel(const TabParams 
 #pragma unroll
       for (int i = 0; i < 16; i++) acc[i] = 0;
 
+      // Inputs are consumed in chunks of CH shards; the next chunk's loads are issued before the
+      // current chunk is coded (2*CH 16-byte loads per thread in flight).
       constexpr int CH = 6;
-      for (int c0 = 0; c0 < n_in; c0 += CH) {
-        uint4 d[CH];
+      uint4 cur[CH], nxt[CH];
+      auto fetch = [&](uint4 (&d)[CH], const int c0) {
 #pragma unroll
         for (int i = 0; i < CH; i++) {
           d[i] = make_uint4(0, 0, 0, 0);
           if (c0 + i < n_in && live) d[i] = ldg_stream(sbase + (size_t)pat_s->in_slot[c0 + i] * p.shard_pitch + col);
         }
+      };
+      fetch(cur, 0);
+      for (int c0 = 0; c0 < n_in; c0 += CH) {
+        if (c0 + CH < n_in) fetch(nxt, c0 + CH);
 #pragma unroll
         for (int i = 0; i < CH; i++) {
           if (c0 + i < n_in) {
-            if (tail) d[i] = keep_head(d[i], tail);
-            const uint32_t* tb = tab + (size_t)(c0 + i) * 256 * R + g;
-            const uint32_t w[4] = {d[i].x, d[i].y, d[i].z, d[i].w};
+            uint4 dd = cur[i];
+            if (tail) dd = keep_head(dd, tail);
+            const int cc = c0 + i;
+            const uint32_t tb = tab_s + (uint32_t)(cc / SPR) * 65536u + (uint32_t)((cc % SPR) * (4 * R) + g * 4);
+            const uint32_t w[4] = {dd.x, dd.y, dd.z, dd.w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-              acc[q * 4 + 0] ^= tb[(w[q] & 0xff) * R];
-              acc[q * 4 + 1] ^= tb[((w[q] >> 8) & 0xff) * R];
-              acc[q * 4 + 2] ^= tb[((w[q] >> 16) & 0xff) * R];
-              acc[q * 4 + 3] ^= tb[(w[q] >> 24) * R];
+              acc[q * 4 + 0] ^= lds_u32(row_addr(byte_of<0>(w[q]), tb));
+              acc[q * 4 + 1] ^= lds_u32(row_addr(byte_of<1>(w[q]), tb));
+              acc[q * 4 + 2] ^= lds_u32(row_addr(byte_of<2>(w[q]), tb));
+              acc[q * 4 + 3] ^= lds_u32(row_addr(byte_of<3>(w[q]), tb));
             }
             if (crc_in) {
-              uint32_t* st = crc_st + (size_t)(c0 + i) * NT + tid;
-              *st = crc_constmul(*st, crc_sh) ^ crc_piece(d[i], crc_sl);
+              uint32_t* st = crc_st + (size_t)cc * NT + tid;
+              *st = crc_constmul(*st, crc_sh) ^ crc_piece(dd, crc_sl);
             }
           }
         }
+#pragma unroll
+        for (int i = 0; i < CH; i++) cur[i] = nxt[i];
       }
       // unpack: output r, word q = byte r of acc[q*4 + 0..3]
       for (int r = 0; r < n_out; r++) {
@@ -312,7 +347,8 @@ static size_t tab_smem_bytes(int n_in, int R, bool with_crc, int n_crc_slots) {
     off += (size_t)n_crc_slots * (kTabThreads / 32) * 4;
     off = (off + 127) & ~(size_t)127;
   }
-  off += (size_t)n_in * 256 * R * 4;
+  const int spr = 64 / R;
+  off += (size_t)((n_in + spr - 1) / spr) * 65536;
   return off;
 }
 

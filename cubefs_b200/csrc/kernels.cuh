@@ -125,6 +125,7 @@ struct BsParams {
   const uint32_t* fold_tables;        // global: [4][256] register * x^(8*(tile - piece))
   const uint32_t* kthread;            // global: [kBsThreads] x^(8*(tile - piece*(tid+1)))
   uint32_t poly;
+  uint32_t k65536;                    // = 65536, opaque to the compiler (see slice4 in bitslice.cu)
 };
 
 

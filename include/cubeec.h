@@ -139,7 +139,8 @@ int cubeec_reconstruct_batch(cubeec_t* h, const cubeec_stripe_t* stripes, size_t
 
 /* A stripe batch already in HBM: shard i of stripe s at d_base + s*stripe_pitch +
  * i*shard_pitch; d_base 16-byte aligned, shard_pitch and stripe_pitch multiples of 16 and
- * shard_pitch >= shard_len.  Bytes [shard_len, shard_pitch) of OUTPUT shards are zeroed.
+ * shard_pitch >= shard_len.  Output bytes from shard_len up to the next 16-byte boundary (32-byte
+ * for 32-aligned layouts) are written as zeros when they fit the pitch; the rest of the pitch is left untouched.
  * d_crc_out (optional, device): n_stripes*(k+m) CRCs.  stream: a cudaStream_t (NULL = the
  * engine's own stream; the call then returns after the work completed). */
 int cubeec_dev_encode(cubeec_t* h, int device, void* d_base, size_t shard_len, size_t shard_pitch,

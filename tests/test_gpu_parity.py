@@ -258,7 +258,7 @@ def test_device_resident_batch(cb, oracle):
         for i in range(n):
             assert (out[s, i, :S] == sh[i]).all(), (s, i)
             assert crc[s, i] == zlib.crc32(sh[i].tobytes()), (s, i)
-        assert (out[s, k:, S:] == 0).all()          # pad bytes of outputs are zeroed
+        assert (out[s, k:, S:(S + 31) // 32 * 32] == 0).all()   # output pad bytes up to the 32-byte boundary are zeroed
     # verify
     dok = torch.zeros(ns, dtype=torch.int32, device="cuda")
     eng.dev_verify(dev.data_ptr(), S, P, n * P, ns, dok.data_ptr())
