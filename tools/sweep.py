@@ -1,0 +1,74 @@
+#!/usr/bin/env python3
+"""BASELINE configs C4/C5: device-resident encode throughput over shard sizes and code modes.
+
+python tools/sweep.py [--gpu 0] [--crc 1]   -> one JSON line per (k, m, S) with GiB/s of data and
+the fraction of the measured HBM peak ((k+m)*S per stripe of algorithmic traffic)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import cubefs_b200 as cb  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def run(eng, k, m, S, crc, total_bytes, dev, steps=5):
+    n = k + m
+    P = (S + 127) // 128 * 128
+    ns = max(1, int(total_bytes // (n * P)))
+    batch = torch.randint(0, 256, (ns, n, P), dtype=torch.uint8, device=dev)
+    dcrc = torch.zeros(ns * n, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def step():
+        eng.dev_encode(batch.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr() if crc else 0, stream=st, device=dev.index)
+    for _ in range(3):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return ns, ms, cb.last_kernel()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpu", type=int, default=0)
+    ap.add_argument("--crc", type=int, default=1)
+    ap.add_argument("--gib", type=float, default=2.0, help="batch size per case (GiB in HBM)")
+    args = ap.parse_args()
+    dev = torch.device("cuda", args.gpu)
+    torch.cuda.set_device(dev)
+    cb.init([args.gpu])
+    pk = peak()
+    cases = [(6, 3, s) for s in (4096, 16384, 65536, 262144, 1 << 20, 4 << 20, 8 << 20)]
+    cases += [(12, 4, s) for s in (4096, 16384, 65536, 262144, 349526, 1 << 20, 4 << 20, 8 << 20)]
+    cases += [(20, 4, 1 << 20), (4, 2, 65536)]
+    engines = {}
+    for (k, m, S) in cases:
+        eng = engines.setdefault((k, m), cb.RSEngine(k, m))
+        for crc in ([0, 1] if args.crc else [0]):
+            ns, ms, kern = run(eng, k, m, S, crc, args.gib * (1 << 30), dev)
+            moved = (k + m) * S * ns / (ms * 1e-3) / 1e9
+            print(json.dumps({"k": k, "m": m, "shard_bytes": S, "stripes": ns, "crc": bool(crc), "kernel": kern,
+                              "ms": round(ms, 4), "data_GiB_s": round(k * S * ns / (ms * 1e-3) / 2**30, 1),
+                              "moved_GB_s": round(moved, 1), "frac_of_measured_hbm": round(moved / pk, 4)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
