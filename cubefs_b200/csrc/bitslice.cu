@@ -325,6 +325,203 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Bit-sliced syndrome reconstruct (see RecPattern in kernels.cuh).  Per 32-byte column:
+//   present data shards  -> transpose -> fixed XOR network (all M rows at once)
+//   syndrome parity rows -> transpose -> XOR into their accumulator rows
+//   needed rows (syndromes, T_p) transposed back to bytes
+//   outputs = per-pattern 4x4 coefficient product of the syndromes through packed shared-memory
+//   tables (one lookup per syndrome byte), T_p XORed into regenerated parity.
+// ------------------------------------------------------------------------------------------
+constexpr int kRecCopies = 16;                       // table copies (copy = lane % 16)
+constexpr size_t kRecSmemBytes = 65536 + 1024 + 1024;
+
+template <int K, int M>
+__global__ void __launch_bounds__(kBsThreads, 1) rs_bsrec_kernel(const BsRecParams p) {
+  using Net = BsNet<K, M>;
+  constexpr int NT = kBsThreads;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* tab = smem;                                              // 256 rows x (4 syndromes x 16 copies) u32 = 64 KiB
+  GfDeviceTables* gf_s = reinterpret_cast<GfDeviceTables*>(smem + 65536);
+  RecPattern* pat_s = reinterpret_cast<RecPattern*>(smem + 65536 + 1024);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t tab_lane = smem_addr(tab) + (uint32_t)((lane & (kRecCopies - 1)) * 4);
+
+  for (int i = tid; i < (int)(sizeof(GfDeviceTables) / 4); i += NT)
+    reinterpret_cast<uint32_t*>(gf_s)[i] = reinterpret_cast<const uint32_t*>(p.gf)[i];
+
+  uint32_t cur_pattern = 0xFFFFFFFFu;
+  const uint32_t n_items = p.n_stripes * p.n_seg;
+  const size_t seg_bytes = (size_t)p.tiles_per_seg * kBsTile;
+
+  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t s = item / p.n_seg, seg = item - s * p.n_seg;
+    const uint32_t pat_id = p.pattern_of_stripe ? p.pattern_of_stripe[s] : 0u;
+    if (pat_id != cur_pattern) {
+      __syncthreads();
+      cur_pattern = pat_id;
+      if (tid < (int)(sizeof(RecPattern) / 4)) reinterpret_cast<uint32_t*>(pat_s)[tid] = reinterpret_cast<const uint32_t*>(p.patterns + pat_id)[tid];
+      __syncthreads();
+      // packed product tables: entry(i, v) = sum_j (coef[j][i] * v) << 8j
+      for (int idx = tid; idx < 4 * 256; idx += NT) {
+        const int i = idx >> 8, v = idx & 255;
+        uint32_t e = 0;
+        if (v && i < pat_s->n_syn) {
+          const int lv = gf_s->log[v];
+          for (int j = 0; j < pat_s->n_out; j++) {
+            const int co = pat_s->coef[j][i];
+            if (co) e |= (uint32_t)gf_s->exp[gf_s->log[co] + lv] << (8 * j);
+          }
+        }
+        uint32_t* row = reinterpret_cast<uint32_t*>(tab + (size_t)v * 256 + (size_t)i * (4 * kRecCopies));
+#pragma unroll
+        for (int q = 0; q < kRecCopies; q++) row[q] = e;
+      }
+      __syncthreads();
+    }
+    const uint32_t data_mask = pat_s->data_mask;
+    const uint32_t syn_mask = pat_s->syn_mask, t_mask = pat_s->t_mask;
+    const int n_out = pat_s->n_out;
+    if (n_out == 0) continue;
+    uint8_t* sbase = p.base + (size_t)s * p.stripe_pitch;
+    const uint32_t T = (seg == p.n_seg - 1) ? p.tiles_last : p.tiles_per_seg;
+    const size_t seg_start = (size_t)seg * seg_bytes;
+
+    for (uint32_t t = 0; t < T; t++) {
+#pragma unroll 1
+      for (int g = 0; g < kBsGroups; g++) {
+        const size_t col = seg_start + (size_t)t * kBsTile + (size_t)tid * kBsPiece + (size_t)g * 32;
+        const bool live = col < p.shard_len;
+        const int tail = (live && col + 32 > p.shard_len) ? (int)(p.shard_len - col) : 0;
+        uint32_t acc[8 * M];
+#pragma unroll
+        for (int i = 0; i < 8 * M; i++) acc[i] = 0;
+        uint32_t bufA[8], bufB[8], bufC[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) bufA[i] = bufB[i] = bufC[i] = 0;
+        const uint8_t* src = sbase + col;
+        auto mask_tail = [&](uint32_t (&w)[8]) {
+          if (tail) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int rem = tail - 4 * i;
+              if (rem <= 0) w[i] = 0;
+              else if (rem < 4) w[i] &= (1u << (8 * rem)) - 1u;
+            }
+          }
+        };
+        auto fetch = [&](const int c, uint32_t (&w)[8]) {
+          if (c < K && live && ((data_mask >> c) & 1u)) ldg256(src + (size_t)c * p.shard_pitch, w);
+        };
+        auto shard = [&](const int c, uint32_t (&w)[8]) {
+          if ((data_mask >> c) & 1u) {   // uniform over the stripe
+            mask_tail(w);
+            bit_transpose8(w);
+            ApplyAt<Net, 0, K>::run(c, w, acc);
+          }
+        };
+        fetch(0, bufA);
+        fetch(1, bufB);
+#pragma unroll
+        for (int c = 0; c < K; c += 3) {
+          fetch(c + 2, bufC);
+          shard(c, bufA);
+          if (c + 1 < K) {
+            fetch(c + 3, bufA);
+            shard(c + 1, bufB);
+          }
+          if (c + 2 < K) {
+            fetch(c + 4, bufB);
+            shard(c + 2, bufC);
+          }
+        }
+        // syndromes: S_r = P_r ^ (network row r)
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+          if ((syn_mask >> r) & 1u) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = 0;
+            if (live) ldg256(src + (size_t)(K + r) * p.shard_pitch, w);
+            mask_tail(w);
+            bit_transpose8(w);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[r * 8 + i] ^= w[i];
+          }
+        }
+        // back to bytes, in place, for the rows that are used
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+          if (((syn_mask | t_mask) >> r) & 1u) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = acc[r * 8 + i];
+            bit_transpose8(w);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[r * 8 + i] = w[i];
+          }
+        }
+        // table stage: packed[q*4+b] = sum over syndromes of entry(i, byte b of word q)
+        uint32_t packed[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) packed[i] = 0;
+        {
+          int si = 0;
+#pragma unroll
+          for (int r = 0; r < M; r++) {
+            if ((syn_mask >> r) & 1u) {
+              const uint32_t tb = tab_lane + (uint32_t)(si * 4 * kRecCopies);
+#pragma unroll
+              for (int q = 0; q < 8; q++) {
+                const uint32_t w = acc[r * 8 + q];
+                uint32_t a0, a1, a2, a3;
+                asm("prmt.b32 %0, %1, 0, 0x4440;" : "=r"(a0) : "r"(w));
+                asm("prmt.b32 %0, %1, 0, 0x4441;" : "=r"(a1) : "r"(w));
+                asm("prmt.b32 %0, %1, 0, 0x4442;" : "=r"(a2) : "r"(w));
+                asm("prmt.b32 %0, %1, 0, 0x4443;" : "=r"(a3) : "r"(w));
+                packed[q * 4 + 0] ^= lds32(a0 * 256u + tb);
+                packed[q * 4 + 1] ^= lds32(a1 * 256u + tb);
+                packed[q * 4 + 2] ^= lds32(a2 * 256u + tb);
+                packed[q * 4 + 3] ^= lds32(a3 * 256u + tb);
+              }
+              si++;
+            }
+          }
+        }
+        // unpack output j, add T_p for regenerated parity, store
+        for (int j = 0; j < n_out; j++) {
+          uint32_t o[8];
+          const uint32_t sel = 0x0040u | (uint32_t)j | ((uint32_t)j << 4);
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const uint32_t lo = prmt(packed[q * 4 + 0], packed[q * 4 + 1], sel);
+            const uint32_t hi = prmt(packed[q * 4 + 2], packed[q * 4 + 3], sel);
+            o[q] = prmt(lo, hi, 0x5410u);
+          }
+          const int prow = pat_s->out_prow[j];
+#pragma unroll
+          for (int r = 0; r < M; r++) {
+            if (prow == r) {
+#pragma unroll
+              for (int q = 0; q < 8; q++) o[q] ^= acc[r * 8 + q];
+            }
+          }
+          if (live) stg256(sbase + (size_t)pat_s->out_slot[j] * p.shard_pitch + col, o);
+        }
+      }
+    }
+  }
+}
+
+template <int K, int M>
+static cudaError_t launch_rec_cfg(const BsRecParams& p, int grid, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(rs_bsrec_kernel<K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecSmemBytes);
+  if (e != cudaSuccess) return e;
+  rs_bsrec_kernel<K, M><<<grid, kBsThreads, kRecSmemBytes, st>>>(p);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // host-side dispatch
 // ------------------------------------------------------------------------------------------
@@ -356,6 +553,14 @@ bool bs_supported(int k, int m, const uint8_t* parity_rows) {
   CUBEEC_BS_CONFIGS(X)
 #undef X
   return false;
+}
+
+cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStream_t st) {
+#define X(KK, MM) \
+  if (k == KK && m == MM) return launch_rec_cfg<KK, MM>(p, grid, st);
+  CUBEEC_BS_CONFIGS(X)
+#undef X
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_bs(int k, int m, const BsParams& p, bool crc, int grid, cudaStream_t st) {

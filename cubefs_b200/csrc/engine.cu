@@ -263,6 +263,7 @@ struct cubeec {
     bool data_only = false;
     std::vector<uint8_t> present;
     Pattern* d_pat = nullptr;
+    RecPattern* d_rec = nullptr;      // bit-sliced syndrome reconstruct patterns (instead of d_pat)
     uint32_t* d_pos = nullptr;
     size_t n_pass = 0, n_pat = 0;
     std::vector<int> nin;
@@ -337,6 +338,54 @@ int decode_passes(cubeec* h, const uint8_t* present, bool data_only, std::vector
   std::lock_guard<std::mutex> lk(h->mu);
   if (h->dec_cache.size() > 8192) h->dec_cache.clear();
   h->dec_cache[key] = passes;
+  return CUBEEC_OK;
+}
+
+// Presence pattern -> syndrome-decode pattern for rs_bsrec_kernel (see RecPattern in kernels.cuh).
+int rec_pattern(cubeec* h, const uint8_t* present, bool data_only, RecPattern& rp) {
+  const int k = h->k, m = h->m;
+  std::memset(&rp, 0, sizeof(rp));
+  std::memset(rp.out_prow, 0xff, sizeof(rp.out_prow));
+  std::vector<int> Ed, R, Ep;
+  int n_present = 0;
+  for (int i = 0; i < k + m; i++) n_present += present[i] ? 1 : 0;
+  for (int c = 0; c < k; c++) {
+    if (present[c]) rp.data_mask |= 1u << c;
+    else Ed.push_back(c);
+  }
+  if (n_present == k + m || (data_only && Ed.empty())) return CUBEEC_OK;   // nothing to do (n_out = 0)
+  if (n_present < k) return CUBEEC_ERR_TOO_FEW_SHARDS;
+  for (int r = 0; r < m; r++) {
+    if (present[k + r]) { if (R.size() < Ed.size()) R.push_back(r); }
+    else if (!data_only) Ep.push_back(r);
+  }
+  if (R.size() < Ed.size()) return CUBEEC_ERR_TOO_FEW_SHARDS;
+  const int ed = (int)Ed.size();
+  if (ed + (int)Ep.size() > 4 || ed > 4) return CUBEEC_ERR_UNSUPPORTED;
+  const Gf256& G = gf();
+  std::vector<uint8_t> A((size_t)ed * ed), Ainv((size_t)ed * ed);
+  for (int i = 0; i < ed; i++)
+    for (int j = 0; j < ed; j++) A[(size_t)i * ed + j] = h->gen[(size_t)(k + R[i]) * k + Ed[j]];
+  if (ed && !gf_invert(A.data(), ed, Ainv.data())) return CUBEEC_ERR_SINGULAR;
+  rp.n_syn = (uint8_t)ed;
+  for (int r : R) rp.syn_mask |= (uint8_t)(1u << r);
+  int j = 0;
+  for (int a = 0; a < ed; a++, j++) {   // missing data shard Ed[a] = sum_i Ainv[a][i] * S_{R[i]}
+    rp.out_slot[j] = (uint8_t)Ed[a];
+    for (int i = 0; i < ed; i++) rp.coef[j][i] = Ainv[(size_t)a * ed + i];
+  }
+  for (int pr : Ep) {                   // missing parity row pr = T_pr + sum_a M[pr][Ed[a]] * D_{Ed[a]}
+    rp.out_slot[j] = (uint8_t)(k + pr);
+    rp.out_prow[j] = (uint8_t)pr;
+    rp.t_mask |= (uint8_t)(1u << pr);
+    for (int i = 0; i < ed; i++) {
+      uint8_t v = 0;
+      for (int a = 0; a < ed; a++) v ^= G.mul(h->gen[(size_t)(k + pr) * k + Ed[a]], Ainv[(size_t)a * ed + i]);
+      rp.coef[j][i] = v;
+    }
+    j++;
+  }
+  rp.n_out = (uint8_t)j;
   return CUBEEC_OK;
 }
 
@@ -637,6 +686,7 @@ extern "C" void cubeec_destroy(cubeec_t* h) {
   for (auto& pl : h->plans) {
     cudaSetDevice(pl->device);
     if (pl->d_pat) cudaFree(pl->d_pat);
+    if (pl->d_rec) cudaFree(pl->d_rec);
     if (pl->d_pos) cudaFree(pl->d_pos);
   }
   for (size_t ci = 0; ci < h->d_enc.size() && ci < g.ctx.size(); ci++) {
@@ -755,7 +805,75 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
         break;
       }
   }
+  const bool use_rec = h->bs_ok && h->m <= 4 && g_force_kernel.load() != 1 &&
+                       bs_layout_ok((const uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch);
+  if (plan && use_rec != (plan->d_rec != nullptr)) plan = nullptr;
   std::unique_ptr<cubeec::Plan> fresh;
+  if (!plan && use_rec) {
+    std::map<std::string, uint32_t> ids;
+    std::vector<RecPattern> pats;
+    std::vector<uint32_t> pos(n_stripes);
+    for (size_t s = 0; s < n_stripes; s++) {
+      std::string key((const char*)present + s * n, (size_t)n);
+      for (auto& ch : key) ch = ch ? 1 : 0;
+      auto it = ids.find(key);
+      if (it == ids.end()) {
+        RecPattern rp;
+        rc = rec_pattern(h, (const uint8_t*)key.data(), data_only != 0, rp);
+        if (rc) return rc;
+        it = ids.emplace(key, (uint32_t)pats.size()).first;
+        pats.push_back(rp);
+      }
+      pos[s] = it->second;
+    }
+    fresh = std::make_unique<cubeec::Plan>();
+    fresh->device = device;
+    fresh->data_only = data_only != 0;
+    fresh->present.assign(present, present + n_stripes * (size_t)n);
+    fresh->n_pat = pats.size();
+    CU(cudaMalloc(&fresh->d_rec, pats.size() * sizeof(RecPattern)));
+    CU(cudaMalloc(&fresh->d_pos, n_stripes * sizeof(uint32_t)));
+    CU(cudaMemcpy(fresh->d_rec, pats.data(), pats.size() * sizeof(RecPattern), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(fresh->d_pos, pos.data(), n_stripes * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    plan = fresh.get();
+  }
+  if (plan && plan->d_rec) {
+    LaneLease lease2;
+    cudaStream_t st2 = (cudaStream_t)stream;
+    if (!st2) {
+      if ((rc = lease2.acquire(c))) return rc;
+      st2 = lease2.lane->stream;
+    }
+    const Geometry gm = pick_geometry(*c, shard_len, n_stripes, plan->n_pat > 1, kBsTile);
+    BsRecParams rp;
+    std::memset(&rp, 0, sizeof(rp));
+    rp.base = (uint8_t*)d_base;
+    rp.stripe_pitch = stripe_pitch;
+    rp.shard_pitch = shard_pitch;
+    rp.shard_len = (uint32_t)shard_len;
+    rp.n_stripes = (uint32_t)n_stripes;
+    rp.n_seg = gm.n_seg;
+    rp.tiles_per_seg = gm.tiles_per_seg;
+    rp.tiles_last = gm.tiles_last;
+    rp.patterns = plan->d_rec;
+    rp.pattern_of_stripe = plan->d_pos;
+    rp.gf = c->d_gf;
+    CU(launch_bs_rec(h->k, h->m, rp, gm.grid, st2));
+    g_launches++;
+    t_last_kernel = "rs_bsrec_kernel";
+    if (fresh) {
+      std::lock_guard<std::mutex> lk(h->mu);
+      if (h->plans.size() < 16) {
+        h->plans.push_back(std::move(fresh));
+      } else {
+        CU(cudaStreamSynchronize(st2));
+        cudaFree(fresh->d_rec);
+        cudaFree(fresh->d_pos);
+      }
+    }
+    if (!stream) CU(cudaStreamSynchronize(st2));
+    return CUBEEC_OK;
+  }
   if (!plan) {
     // distinct presence patterns -> pattern ids
     std::map<std::string, uint32_t> ids;

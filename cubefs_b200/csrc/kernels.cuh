@@ -129,7 +129,39 @@ struct BsParams {
 };
 
 
+// ---- bit-sliced syndrome reconstruct (bitslice.cu) ---------------------------------------------
+// The reference decodes from the first k present shards (RS/reedsolomon.go:1453-1465).  Data indices
+// precede parity indices, so that set is: every present data shard + the first e_d present parity
+// shards (e_d = missing data shards).  With the FIXED encode network, syndromes
+//   S_r = P_r ^ sum_{c present} M[r][c] D_c = sum_{c missing} M[r][c] D_c        (r in those e_d parity rows)
+// determine the missing data through the tiny e_d x e_d inverse; missing parity p follows as
+//   P_p = T_p ^ sum_{c missing} M[p][c] D_c,   T_p = sum_{c present} M[p][c] D_c  (same network pass).
+// Same k shards in, so results are identical to the reference even on inconsistent input.
+struct alignas(16) RecPattern {
+  uint32_t data_mask;      // bit c set: data shard c is present (read it)
+  uint8_t n_syn;           // e_d: syndromes used
+  uint8_t n_out;           // shards regenerated (<= 4)
+  uint8_t syn_mask;        // bit r set: parity row r supplies a syndrome
+  uint8_t t_mask;          // bit p set: parity row p is missing and wanted (needs T_p)
+  uint8_t out_slot[4];     // shard slot of output j
+  uint8_t out_prow[4];     // parity row of output j, 0xff for a data shard
+  uint8_t coef[4][4];      // coef[j][i]: output j += coef * (i-th syndrome, in increasing row order)
+  uint8_t pad[12];
+};
+static_assert(sizeof(RecPattern) == 48, "RecPattern layout");
+
+struct BsRecParams {
+  uint8_t* base;
+  size_t stripe_pitch, shard_pitch;
+  uint32_t shard_len, n_stripes;
+  uint32_t n_seg, tiles_per_seg, tiles_last;
+  const RecPattern* patterns;
+  const uint32_t* pattern_of_stripe;
+  const GfDeviceTables* gf;
+};
+
 bool bs_supported(int k, int m, const uint8_t* parity_rows);   // a specialised network exists for this matrix
+cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStream_t st);
 cudaError_t launch_bs(int k, int m, const BsParams& p, bool crc, int grid, cudaStream_t st);
 
 }  // namespace cbe

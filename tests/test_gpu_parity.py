@@ -353,3 +353,69 @@ def test_kernel_selection_and_ab_equivalence(cb, oracle):
         torch.cuda.synchronize()
         got = view.cpu().numpy().reshape(ns, n, P)
         assert (got[:, :, :S] == outs[0][0][:, :, :S]).all()
+
+
+@pytest.mark.parametrize("km", [(12, 4), (6, 3), (4, 2), (20, 4), (10, 4), (3, 3), (4, 4)])
+def test_device_reconstruct_syndrome_kernel(cb, oracle, km):
+    """cubeec_dev_reconstruct on specialised matrices runs the bit-sliced syndrome kernel; it must agree
+    with the oracle for every erasure shape (data only, parity only, mixed, max), honour data_only, and
+    agree with the generic table kernel even on INCONSISTENT survivors (same k shards are used)."""
+    import torch
+    k, m = km
+    n = k + m
+    rng = np.random.default_rng(k * 17 + m)
+    S = int(rng.integers(3000, 90000))
+    P = (S + 127) // 128 * 128
+    shapes = [[0], [k], [k - 1, n - 1], list(range(m)), list(range(k, n)), [1, k] + ([k + 1] if m > 2 else []), []]
+    shapes += [sorted(rng.choice(n, size=int(rng.integers(1, m + 1)), replace=False).tolist()) for _ in range(12)]
+    ns = len(shapes)
+    host = rng.integers(0, 256, (ns, n, P), dtype=np.uint8)
+    ora = oracle.RS(k, m)
+    for s in range(ns):
+        sh = [host[s, i, :S].copy() for i in range(n)]
+        ora.encode(sh)
+        for i in range(k, n):
+            host[s, i, :S] = sh[i]
+    eng = cb.RSEngine(k, m)
+    present = np.ones((ns, n), dtype=np.uint8)
+    for s, miss in enumerate(shapes):
+        present[s, miss] = 0
+    for data_only in (False, True):
+        broken = host.copy()
+        for s, miss in enumerate(shapes):
+            broken[s, miss, :] = 0xA5
+        dev = torch.from_numpy(broken).cuda()
+        eng.dev_reconstruct(dev.data_ptr(), S, P, n * P, ns, present, data_only=data_only)
+        assert cb.last_kernel() == "rs_bsrec_kernel"
+        torch.cuda.synchronize()
+        got = dev.cpu().numpy()
+        for s, miss in enumerate(shapes):
+            for i in range(n):
+                if data_only and i >= k and i in miss:
+                    assert (got[s, i, :S] == 0xA5).all()          # missing parity stays missing
+                else:
+                    assert (got[s, i, :S] == host[s, i, :S]).all(), (km, s, i, miss, data_only)
+    # inconsistent survivors: corrupt one present shard per stripe, both kernels must produce the same bytes
+    bad = host.copy()
+    for s, miss in enumerate(shapes):
+        bad[s, miss, :] = 0
+        keep = [i for i in range(n) if i not in miss]
+        bad[s, keep[s % len(keep)], 7] ^= 0x5A
+    outs = []
+    for force in (0, 1):
+        cb.force_kernel(force)
+        try:
+            dev = torch.from_numpy(bad).cuda()
+            eng.dev_reconstruct(dev.data_ptr(), S, P, n * P, ns, present)
+            torch.cuda.synchronize()
+            outs.append(dev.cpu().numpy())
+        finally:
+            cb.force_kernel(0)
+    assert (outs[0][:, :, :S] == outs[1][:, :, :S]).all()
+    # too few shards
+    present2 = np.ones((1, n), dtype=np.uint8)
+    present2[0, :m + 1] = 0
+    dev = torch.from_numpy(host[:1].copy()).cuda()
+    with pytest.raises(cb.CubeecError) as e:
+        eng.dev_reconstruct(dev.data_ptr(), S, P, n * P, 1, present2)
+    assert e.value.name == "ErrTooFewShards"
