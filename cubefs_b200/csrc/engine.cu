@@ -28,6 +28,7 @@ using namespace cbe;
 static thread_local std::string t_last_error;
 static thread_local const char* t_last_kernel = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_force_kernel{0};   // cubeec_debug_force_kernel: A/B measurement aid
 
 static int cuda_fail(cudaError_t e, const char* what) {
   t_last_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -423,6 +424,7 @@ Geometry pick_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes, bool
 int run_passes(DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t shard_len, size_t shard_pitch,
                size_t stripe_pitch, size_t n_stripes, int n_slots, const std::vector<const Pattern*>& d_pass_patterns,
                const std::vector<int>& pass_n_in, const std::vector<int>& pass_crc_slots,
+               const std::vector<char>& pass_n_in_exact /* every pattern of the pass has exactly pass_n_in inputs */,
                const uint32_t* d_pattern_of_stripe, int mode, int32_t* d_mismatch, uint32_t* d_crc_part,
                int crc_poly, const Geometry& gm) {
   for (size_t j = 0; j < d_pass_patterns.size(); j++) {
@@ -445,6 +447,12 @@ int run_passes(DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t shard_len
     p.gf = c.d_gf;
     p.crc = c.d_crc[crc_poly ? 1 : 0];
     const bool with_crc = d_crc_part != nullptr;
+    if (!with_crc && pass_n_in_exact[j] && tabk_supported(pass_n_in[j]) && g_force_kernel.load() != 3) {
+      CU(launch_tabk(p, pass_n_in[j], gm.grid, stream));
+      g_launches++;
+      t_last_kernel = "rs_tabk_kernel";
+      continue;
+    }
     size_t smem = 0;
     int R = tab_pick_replication(pass_n_in[j], with_crc, pass_crc_slots[j], c.smem_limit, &smem);
     if (R == 0) return CUBEEC_ERR_UNSUPPORTED;
@@ -526,7 +534,7 @@ bool bs_layout_ok(const uint8_t* d_base, size_t shard_len, size_t shard_pitch, s
   return (((uintptr_t)d_base | shard_pitch | stripe_pitch) & 31) == 0 && shard_pitch >= round_up(shard_len, 32);
 }
 
-std::atomic<int> g_force_kernel{0};   // 0 auto, 1 table kernel only (tests / A-B measurements)
+
 
 // Encode (mode 0) or verify (mode 1) a device-resident batch.  d_part: caller scratch of
 // crc_part_bytes() when CRCs are wanted, or nullptr to use the stream-ordered allocator.
@@ -588,7 +596,8 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
     CU(cudaMallocAsync(&d_part, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
     own = true;
   }
-  int rc = run_passes(c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, n, pp, nin, ncrc, nullptr,
+  const std::vector<char> exact(pp.size(), 1);
+  int rc = run_passes(c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, n, pp, nin, ncrc, exact, nullptr,
                       mode, d_mismatch, want_crc ? d_part : nullptr, crc_poly, gm);
   if (rc) return rc;
   if (want_crc) {
@@ -805,7 +814,9 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
         break;
       }
   }
-  const bool use_rec = h->bs_ok && h->m <= 4 && g_force_kernel.load() != 1 &&
+  // The bit-sliced syndrome kernel is exact but (as measured, profiles/) still slower than the
+  // fixed-arity table kernel on B200; it is opt-in (cubeec_debug_force_kernel(2)) until it wins.
+  const bool use_rec = h->bs_ok && h->m <= 4 && g_force_kernel.load() == 2 &&
                        bs_layout_ok((const uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch);
   if (plan && use_rec != (plan->d_rec != nullptr)) plan = nullptr;
   std::unique_ptr<cubeec::Plan> fresh;
@@ -935,7 +946,8 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
   for (size_t j = 0; j < plan->n_pass; j++) pp.push_back(plan->d_pat + j * plan->n_pat);
   std::vector<int> ncrc(plan->n_pass, 0);
   const Geometry gm = pick_geometry(*c, shard_len, n_stripes, plan->n_pat > 1);
-  rc = run_passes(*c, st, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, n, pp, plan->nin, ncrc,
+  const std::vector<char> exact(plan->n_pass, 1);   // no-op patterns (n_out = 0) are skipped by both kernels
+  rc = run_passes(*c, st, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, n, pp, plan->nin, ncrc, exact,
                   plan->d_pos, 0, nullptr, nullptr, 0, gm);
   if (rc) return rc;
   if (fresh) {
@@ -1065,7 +1077,8 @@ int reconstruct_issue(cubeec* h, DevCtx& c, Lane& l, uint8_t* const* shards, con
       nin.push_back(passes[j].n_in);
       ncrc.push_back(passes[j].n_out);
     }
-    rc = run_passes(c, l.stream, l.d_buf, S, P, P * n, 1, n, pp, nin, ncrc, nullptr, 0, nullptr, d_part, crc_poly, gm);
+    const std::vector<char> exact(pp.size(), 1);
+    rc = run_passes(c, l.stream, l.d_buf, S, P, P * n, 1, n, pp, nin, ncrc, exact, nullptr, 0, nullptr, d_part, crc_poly, gm);
     if (rc) return rc;
     std::vector<uint8_t> enable(n, 0);
     for (auto& ps : passes)

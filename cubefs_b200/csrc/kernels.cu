@@ -339,6 +339,178 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tab_kernel(const TabParams 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fixed-arity variant of the table kernel (no CRC): the number of inputs is a template parameter,
+// so the shard loop is fully unrolled with no predicates, all loads of a column are in flight at
+// once, and pairs of lookups are folded into one 3-input XOR.  Used for reconstruct / verify /
+// unaligned encode of the common code modes; anything else takes rs_tab_kernel.
+// ------------------------------------------------------------------------------------------
+template <int R, int KF>
+__global__ void __launch_bounds__(kTabThreads, 1) rs_tabk_kernel(const TabParams p) {
+  constexpr int NT = kTabThreads;
+  constexpr int SPR = 64 / R;
+  constexpr int CH = KF <= 12 ? KF : (KF + 1) / 2;     // inputs loaded per chunk
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  GfDeviceTables* gf_s = reinterpret_cast<GfDeviceTables*>(smem + 16);
+  Pattern* pat_s = reinterpret_cast<Pattern*>(smem + 16 + sizeof(GfDeviceTables));
+  uint8_t* tab = smem + ((16 + sizeof(GfDeviceTables) + sizeof(Pattern) + 127) & ~(size_t)127);
+  const uint32_t tab_s = smem_u32(tab);
+  const int tid = threadIdx.x;
+  const int g = (tid & 31) % R;
+
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, sizeof(GfDeviceTables));
+    bulk_g2s(gf_s, p.gf, sizeof(GfDeviceTables), bar);
+  }
+  mbar_wait(bar, 0);
+
+  uint32_t cur_pattern = 0xFFFFFFFFu;
+  const uint32_t n_items = p.n_stripes * p.n_seg;
+  const size_t seg_bytes = (size_t)p.tiles_per_seg * kTabTile;
+
+  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t s = item / p.n_seg, seg = item - s * p.n_seg;
+    const uint32_t pat_id = p.pattern_of_stripe ? p.pattern_of_stripe[s] : 0u;
+    if (pat_id != cur_pattern) {
+      __syncthreads();
+      cur_pattern = pat_id;
+      const uint4* src = reinterpret_cast<const uint4*>(p.patterns + pat_id);
+      uint4* dst = reinterpret_cast<uint4*>(pat_s);
+      for (int i = tid; i < (int)(sizeof(Pattern) / 16); i += NT) dst[i] = src[i];
+      __syncthreads();
+      const int n_out = pat_s->n_out;
+      for (int idx = tid; idx < KF * 256; idx += NT) {
+        const int c = idx >> 8, v = idx & 255;
+        uint32_t e = 0;
+        if (v) {
+          const int lv = gf_s->log[v];
+          for (int r = 0; r < n_out; r++) {
+            const int co = pat_s->coef[r][c];
+            if (co) e |= (uint32_t)gf_s->exp[gf_s->log[co] + lv] << (8 * r);
+          }
+        }
+        uint32_t* row = reinterpret_cast<uint32_t*>(tab + (size_t)(c / SPR) * 65536 + (size_t)v * 256 + (size_t)(c % SPR) * (4 * R));
+#pragma unroll
+        for (int q = 0; q < R; q++) row[q] = e;
+      }
+      __syncthreads();
+    }
+    const int n_out = pat_s->n_out;
+    if (n_out == 0) continue;
+    uint8_t* sbase = p.base + (size_t)s * p.stripe_pitch;
+    const uint32_t T = (seg == p.n_seg - 1) ? p.tiles_last : p.tiles_per_seg;
+    const size_t seg_start = (size_t)seg * seg_bytes;
+    // per-input source offsets are stripe constants
+    size_t in_off[KF];
+#pragma unroll
+    for (int c = 0; c < KF; c++) in_off[c] = (size_t)pat_s->in_slot[c] * p.shard_pitch;
+    bool bad = false;
+
+    for (uint32_t t = 0; t < T; t++) {
+      const size_t col = seg_start + (size_t)t * kTabTile + (size_t)tid * kPiece;
+      const bool live = col < p.shard_len;
+      const int tail = (live && col + kPiece > p.shard_len) ? (int)(p.shard_len - col) : 0;
+      uint32_t acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) acc[i] = 0;
+#pragma unroll
+      for (int c0 = 0; c0 < KF; c0 += CH) {
+        uint4 d[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+          d[i] = make_uint4(0, 0, 0, 0);
+          if (c0 + i < KF && live) d[i] = ldg_stream(sbase + in_off[c0 + i] + col);
+        }
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < CH; i++) d[i] = keep_head(d[i], tail);
+        }
+        // two inputs per step: acc ^= t_a ^ t_b is one LOP3
+#pragma unroll
+        for (int i = 0; i < CH; i += 2) {
+          const int ca = c0 + i, cb = c0 + i + 1;
+          if (ca < KF) {
+            const bool two = (i + 1 < CH) && (cb < KF);
+            const uint32_t ta = tab_s + (uint32_t)(ca / SPR) * 65536u + (uint32_t)((ca % SPR) * (4 * R) + g * 4);
+            const uint32_t tb = tab_s + (uint32_t)((two ? cb : ca) / SPR) * 65536u + (uint32_t)(((two ? cb : ca) % SPR) * (4 * R) + g * 4);
+            const uint32_t wa[4] = {d[i].x, d[i].y, d[i].z, d[i].w};
+            const uint4 db = d[two ? i + 1 : i];
+            const uint32_t wb[4] = {db.x, db.y, db.z, db.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              if (two) {
+                acc[q * 4 + 0] ^= lds_u32(row_addr(byte_of<0>(wa[q]), ta)) ^ lds_u32(row_addr(byte_of<0>(wb[q]), tb));
+                acc[q * 4 + 1] ^= lds_u32(row_addr(byte_of<1>(wa[q]), ta)) ^ lds_u32(row_addr(byte_of<1>(wb[q]), tb));
+                acc[q * 4 + 2] ^= lds_u32(row_addr(byte_of<2>(wa[q]), ta)) ^ lds_u32(row_addr(byte_of<2>(wb[q]), tb));
+                acc[q * 4 + 3] ^= lds_u32(row_addr(byte_of<3>(wa[q]), ta)) ^ lds_u32(row_addr(byte_of<3>(wb[q]), tb));
+              } else {
+                acc[q * 4 + 0] ^= lds_u32(row_addr(byte_of<0>(wa[q]), ta));
+                acc[q * 4 + 1] ^= lds_u32(row_addr(byte_of<1>(wa[q]), ta));
+                acc[q * 4 + 2] ^= lds_u32(row_addr(byte_of<2>(wa[q]), ta));
+                acc[q * 4 + 3] ^= lds_u32(row_addr(byte_of<3>(wa[q]), ta));
+              }
+            }
+          }
+        }
+      }
+      for (int r = 0; r < n_out; r++) {
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const uint32_t lo = __byte_perm(acc[q * 4 + 0], acc[q * 4 + 1], 0x0040 | r | (r << 4));
+          const uint32_t hi = __byte_perm(acc[q * 4 + 2], acc[q * 4 + 3], 0x0040 | r | (r << 4));
+          o[q] = __byte_perm(lo, hi, 0x5410);
+        }
+        const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
+        uint8_t* optr = sbase + (size_t)pat_s->out_slot[r] * p.shard_pitch + col;
+        if (p.mode == 0) {
+          if (live) stg_stream(optr, ov);
+        } else if (live) {
+          uint4 e = ldg_stream(optr);
+          if (tail) e = keep_head(e, tail);
+          bad |= (e.x != ov.x) | (e.y != ov.y) | (e.z != ov.z) | (e.w != ov.w);
+        }
+      }
+    }
+    if (p.mode == 1 && bad) atomicExch(&p.mismatch[s], 1);
+  }
+}
+
+static size_t tabk_smem_bytes(int kf, int R) {
+  const int spr = 64 / R;
+  return ((16 + sizeof(GfDeviceTables) + sizeof(Pattern) + 127) & ~(size_t)127) + (size_t)((kf + spr - 1) / spr) * 65536;
+}
+
+template <int R, int KF>
+static cudaError_t launch_tabk_cfg(const TabParams& p, int grid, cudaStream_t stream) {
+  const size_t smem = tabk_smem_bytes(KF, R);
+  cudaError_t e = cudaFuncSetAttribute(rs_tabk_kernel<R, KF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  rs_tabk_kernel<R, KF><<<grid, kTabThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// (n_in -> replication) pairs with a fixed-arity instantiation
+#define CUBEEC_TABK_CONFIGS(X) X(16, 3) X(16, 4) X(16, 5) X(16, 6) X(16, 8) X(16, 10) X(16, 12) X(8, 15) X(8, 16) X(8, 20) X(8, 24)
+
+bool tabk_supported(int n_in) {
+#define X(RR, KK) if (n_in == KK) return true;
+  CUBEEC_TABK_CONFIGS(X)
+#undef X
+  return false;
+}
+
+cudaError_t launch_tabk(const TabParams& p, int n_in, int grid, cudaStream_t stream) {
+#define X(RR, KK) if (n_in == KK) return launch_tabk_cfg<RR, KK>(p, grid, stream);
+  CUBEEC_TABK_CONFIGS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
 static size_t tab_smem_bytes(int n_in, int R, bool with_crc, int n_crc_slots) {
   size_t off = 16 + sizeof(GfDeviceTables) + sizeof(Pattern);
   if (with_crc) {

@@ -79,6 +79,9 @@ int tab_pick_replication(int n_in, bool with_crc, int n_crc_slots, size_t smem_l
 cudaError_t launch_tab(const TabParams& p, int replication, bool with_crc, int n_crc_slots,
                        size_t smem_bytes, int grid, cudaStream_t stream);
 cudaError_t launch_crc_finalize(const CrcFinalizeParams& p, cudaStream_t stream);
+// fixed-arity fast path of the table kernel (no CRC); every pattern of the launch must have n_in inputs
+bool tabk_supported(int n_in);
+cudaError_t launch_tabk(const TabParams& p, int n_in, int grid, cudaStream_t stream);
 cudaError_t tab_configure(size_t* smem_limit_out);   // sets max dynamic smem attributes
 
 cudaError_t launch_invert_flags(int32_t* flags, size_t n, cudaStream_t stream);   // flags[i] = !flags[i]

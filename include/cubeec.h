@@ -175,7 +175,8 @@ int cubeec_dev_crc32(int device, const void* d_base, size_t len, size_t pitch, s
 uint64_t cubeec_kernel_launches(void);
 /* Name of the kernel variant the last dev_* call on this thread dispatched to. */
 const char* cubeec_last_kernel(void);
-/* Measurement aid: 0 = automatic kernel choice (default), 1 = generic table kernel only. */
+/* Measurement aid: 0 = automatic kernel choice (default), 1 = no bit-sliced kernels, 2 = bit-sliced
+ * syndrome kernel for cubeec_dev_reconstruct, 3 = generic (runtime-arity) table kernel only. */
 void cubeec_debug_force_kernel(int which);
 
 #ifdef __cplusplus

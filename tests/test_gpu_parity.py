@@ -321,7 +321,7 @@ def test_kernel_selection_and_ab_equivalence(cb, oracle):
         host = rng.integers(0, 256, (ns, n, P), dtype=np.uint8)
         eng = cb.RSEngine(k, m)
         outs = []
-        for force, want in ((0, "rs_bs_kernel<crc>"), (1, "rs_tab_kernel<crc>")):
+        for force, want in ((0, "rs_bs_kernel<crc>"), (1, "rs_tab_kernel<crc>")):   # CRC always takes the generic table kernel
             cb.force_kernel(force)
             try:
                 dev = torch.from_numpy(host).cuda()
@@ -349,7 +349,7 @@ def test_kernel_selection_and_ab_equivalence(cb, oracle):
         assert view.data_ptr() % 32 == 16
         view.copy_(dev.reshape(-1))
         eng.dev_encode(view.data_ptr(), S, P, n * P, ns)
-        assert cb.last_kernel() == "rs_tab_kernel"
+        assert cb.last_kernel() == "rs_tabk_kernel"
         torch.cuda.synchronize()
         got = view.cpu().numpy().reshape(ns, n, P)
         assert (got[:, :, :S] == outs[0][0][:, :, :S]).all()
@@ -385,7 +385,11 @@ def test_device_reconstruct_syndrome_kernel(cb, oracle, km):
         for s, miss in enumerate(shapes):
             broken[s, miss, :] = 0xA5
         dev = torch.from_numpy(broken).cuda()
-        eng.dev_reconstruct(dev.data_ptr(), S, P, n * P, ns, present, data_only=data_only)
+        cb.force_kernel(2)
+        try:
+            eng.dev_reconstruct(dev.data_ptr(), S, P, n * P, ns, present, data_only=data_only)
+        finally:
+            cb.force_kernel(0)
         assert cb.last_kernel() == "rs_bsrec_kernel"
         torch.cuda.synchronize()
         got = dev.cpu().numpy()
@@ -402,7 +406,7 @@ def test_device_reconstruct_syndrome_kernel(cb, oracle, km):
         keep = [i for i in range(n) if i not in miss]
         bad[s, keep[s % len(keep)], 7] ^= 0x5A
     outs = []
-    for force in (0, 1):
+    for force in (2, 0, 3):   # bit-sliced syndrome kernel, fixed-arity table kernel, generic table kernel
         cb.force_kernel(force)
         try:
             dev = torch.from_numpy(bad).cuda()
@@ -411,7 +415,7 @@ def test_device_reconstruct_syndrome_kernel(cb, oracle, km):
             outs.append(dev.cpu().numpy())
         finally:
             cb.force_kernel(0)
-    assert (outs[0][:, :, :S] == outs[1][:, :, :S]).all()
+    assert (outs[0][:, :, :S] == outs[1][:, :, :S]).all() and (outs[1][:, :, :S] == outs[2][:, :, :S]).all()
     # too few shards
     present2 = np.ones((1, n), dtype=np.uint8)
     present2[0, :m + 1] = 0
