@@ -21,7 +21,8 @@ ERR = {0: "ok", 1: "ErrInvShardNum", 2: "ErrMaxShardNum", 3: "ErrTooFewShards", 
        6: "reedsolomon.ErrShortData", 7: "ErrReconstructRequired", 8: "errSingular", 9: "invalid argument",
        10: "no CUDA device", 11: "CUDA error", 12: "unsupported",
        100: "ErrShortData", 101: "ErrInvalidCodeMode", 102: "ErrVerify", 103: "ErrInvalidShards",
-       110: "ErrMismatchedCrc", 111: "ErrInvalidBlock"}
+       110: "ErrMismatchedCrc", 111: "ErrInvalidBlock", 120: "ErrShardHeaderMagic", 121: "ErrShardHeaderCrc",
+       122: "ErrShardFooterMagic", 123: "ErrShardCrc", 124: "ErrShardSize"}
 
 
 class EcError(RuntimeError):
@@ -62,6 +63,13 @@ def _load() -> C.CDLL:
         L.cubefs_crc32block_encode.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.POINTER(C.c_uint32)]
         L.cubefs_crc32block_decode.restype = C.c_longlong
         L.cubefs_crc32block_decode.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p]
+        L.cubefs_shard_physize.restype = C.c_longlong
+        L.cubefs_shard_physize.argtypes = [C.c_longlong]
+        L.cubefs_shard_write.restype = C.c_longlong
+        L.cubefs_shard_write.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+        L.cubefs_shard_read.restype = C.c_longlong
+        L.cubefs_shard_read.argtypes = [C.c_void_p, C.c_longlong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong),
+                                        C.POINTER(C.c_uint32), C.c_void_p]
         _lib = L
     return _lib
 
@@ -342,3 +350,36 @@ def BlockDecode(src: bytes, blockLen: int = 65536) -> bytes:
     if n < 0:
         raise EcError(n)
     return dst[:n].tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# blobnode shard image (core/shard.go, core/storage/datafile.go)
+# ---------------------------------------------------------------------------------------------
+def Alignphysize(shardSize: int) -> int:
+    return _load().cubefs_shard_physize(shardSize)
+
+
+def AlignSize(p: int, bound: int) -> int:
+    return (p + bound - 1) & ~(bound - 1)
+
+
+def WriteShard(bid: int, vuid: int, data: bytes):
+    """datafile.Write: (on-disk image, shard.Crc); whole-shard and per-block CRCs from one GPU pass."""
+    a = np.frombuffer(data, dtype=np.uint8)
+    out = np.zeros(Alignphysize(len(a)), dtype=np.uint8)
+    crc = C.c_uint32(0)
+    n = _load().cubefs_shard_write(bid, vuid, a.ctypes.data if a.size else None, a.size, out.ctypes.data, C.byref(crc))
+    if n < 0:
+        raise EcError(n)
+    return out[:n].tobytes(), int(crc.value)
+
+
+def ReadShard(image: bytes):
+    """datafile.Read / data inspect: verify header, every block CRC and the footer; -> (bid, vuid, crc, data)."""
+    a = np.frombuffer(image, dtype=np.uint8)
+    out = np.zeros(max(len(a), 1), dtype=np.uint8)
+    bid, vuid, crc = C.c_ulonglong(0), C.c_ulonglong(0), C.c_uint32(0)
+    n = _load().cubefs_shard_read(a.ctypes.data, a.size, C.byref(bid), C.byref(vuid), C.byref(crc), out.ctypes.data)
+    if n < 0:
+        raise EcError(n)
+    return int(bid.value), int(vuid.value), int(crc.value), out[:n].tobytes()

@@ -570,4 +570,67 @@ int Decode(const uint8_t* src, int64_t total, int64_t blockLen, std::vector<uint
 }
 }  // namespace crc32block
 
+// =============================================================================================
+// blobnode shard image
+// =============================================================================================
+namespace blobnode {
+namespace {
+const uint8_t kHeaderMagic[4] = {0xab, 0xcd, 0xef, 0xcc};   // core/shard.go:_shardHeaderMagic
+const uint8_t kFooterMagic[4] = {0xcc, 0xef, 0xcd, 0xab};
+void put_be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+void put_be64(uint8_t* p, uint64_t v) { put_be32(p, (uint32_t)(v >> 32)); put_be32(p + 4, (uint32_t)v); }
+uint32_t get_be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+uint64_t get_be64(const uint8_t* p) { return ((uint64_t)get_be32(p) << 32) | get_be32(p + 4); }
+}  // namespace
+
+int64_t Alignphysize(int64_t shardSize) { return kHeaderSize + crc32block::EncodeSize(shardSize, crc32block::kDefaultBlock) + kFooterSize; }
+int64_t AlignSize(int64_t p, int64_t bound) { return (p + bound - 1) & ~(bound - 1); }
+
+// Shard.WriterHeader (core/shard.go:241-261) + datafile.Write (storage/datafile.go:304-408) + WriterFooter (:263-274)
+int WriteShard(ShardMeta& meta, const uint8_t* data, std::vector<uint8_t>& image) {
+  std::vector<uint8_t> body;
+  uint32_t whole = 0;
+  int rc = crc32block::Encode(data, meta.Size, crc32block::kDefaultBlock, body, &whole);
+  if (rc) return rc;
+  meta.Crc = whole;
+  image.assign((size_t)Alignphysize(meta.Size), 0);
+  uint8_t* h = image.data();
+  std::memcpy(h + 4, kHeaderMagic, 4);
+  put_be64(h + 8, meta.Bid);
+  put_be64(h + 16, meta.Vuid);
+  put_be32(h + 24, meta.Size);
+  put_be32(h + 28, 0);
+  uint32_t hcrc = 0;
+  if ((rc = cubeec_crc32(h + 4, 28, CUBEEC_CRC_IEEE, &hcrc))) return rc;   // headerCrc := crc32.ChecksumIEEE(buf[4:])
+  put_be32(h, hcrc);
+  std::memcpy(h + kHeaderSize, body.data(), body.size());
+  uint8_t* f = h + kHeaderSize + body.size();
+  std::memcpy(f, kFooterMagic, 4);
+  put_be32(f + 4, whole);
+  return 0;
+}
+
+// Shard.ParseHeader (core/shard.go:276-297) + block decode (blockUnit.check) + footer check
+int ReadShard(const uint8_t* image, int64_t n, ShardMeta& meta, std::vector<uint8_t>& data) {
+  if (n < kHeaderSize + kFooterSize) return ErrShardSize;
+  if (std::memcmp(image + 4, kHeaderMagic, 4) != 0) return ErrShardHeaderMagic;
+  uint32_t hcrc = 0;
+  int rc = cubeec_crc32(image + 4, 28, CUBEEC_CRC_IEEE, &hcrc);
+  if (rc) return rc;
+  if (hcrc != get_be32(image)) return ErrShardHeaderCrc;
+  meta.Bid = get_be64(image + 8);
+  meta.Vuid = get_be64(image + 16);
+  meta.Size = get_be32(image + 24);
+  if (Alignphysize(meta.Size) != n) return ErrShardSize;
+  const int64_t body = n - kHeaderSize - kFooterSize;
+  if ((rc = crc32block::Decode(image + kHeaderSize, body, crc32block::kDefaultBlock, data))) return rc;
+  const uint8_t* f = image + kHeaderSize + body;
+  if (std::memcmp(f, kFooterMagic, 4) != 0) return ErrShardFooterMagic;
+  meta.Crc = get_be32(f + 4);
+  uint32_t whole = 0;
+  if ((rc = cubeec_crc32(data.data(), data.size(), CUBEEC_CRC_IEEE, &whole))) return rc;
+  return whole == meta.Crc ? 0 : ErrShardCrc;
+}
+}  // namespace blobnode
+
 }  // namespace cubefs

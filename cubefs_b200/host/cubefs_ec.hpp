@@ -110,4 +110,18 @@ int Encode(const uint8_t* src, int64_t n, int64_t blockLen, std::vector<uint8_t>
 int Decode(const uint8_t* src, int64_t total, int64_t blockLen, std::vector<uint8_t>& dst);
 }  // namespace crc32block
 
+// blobstore/blobnode/core: the on-disk shard image (core/shard.go:74-112,241-297; storage/datafile.go:304-445)
+namespace blobnode {
+constexpr int kHeaderSize = 32, kFooterSize = 8;
+enum : int { ErrShardHeaderMagic = 120, ErrShardHeaderCrc = 121, ErrShardFooterMagic = 122, ErrShardCrc = 123, ErrShardSize = 124 };
+int64_t Alignphysize(int64_t shardSize);                       // core/shard.go:419-422
+int64_t AlignSize(int64_t p, int64_t bound);                   // page alignment of chunk offsets
+struct ShardMeta { uint64_t Bid = 0, Vuid = 0; uint32_t Size = 0, Crc = 0; };
+// datafile.Write: header | crc32block-framed body | footer.  Both CRC passes of the reference (whole
+// shard + per block) are ONE GPU pass here (cubeec_crc32_blocks).  meta.Crc is filled in.
+int WriteShard(ShardMeta& meta, const uint8_t* data, std::vector<uint8_t>& image);
+// datafile.Read / data inspect: parse header, verify every block CRC and the footer CRC, return data.
+int ReadShard(const uint8_t* image, int64_t n, ShardMeta& meta, std::vector<uint8_t>& data);
+}  // namespace blobnode
+
 }  // namespace cubefs

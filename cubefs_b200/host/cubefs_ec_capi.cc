@@ -150,4 +150,25 @@ long long cubefs_crc32block_decode(const uint8_t* src, long long total, long lon
   return (long long)out.size();
 }
 
+long long cubefs_shard_physize(long long size) { return blobnode::Alignphysize(size); }
+long long cubefs_shard_write(unsigned long long bid, unsigned long long vuid, const uint8_t* data, uint32_t size, uint8_t* out, uint32_t* crc) {
+  blobnode::ShardMeta m;
+  m.Bid = bid; m.Vuid = vuid; m.Size = size;
+  std::vector<uint8_t> img;
+  int rc = blobnode::WriteShard(m, data, img);
+  if (rc) return -rc;
+  std::memcpy(out, img.data(), img.size());
+  *crc = m.Crc;
+  return (long long)img.size();
+}
+long long cubefs_shard_read(const uint8_t* image, long long n, unsigned long long* bid, unsigned long long* vuid, uint32_t* crc, uint8_t* out) {
+  blobnode::ShardMeta m;
+  std::vector<uint8_t> data;
+  int rc = blobnode::ReadShard(image, n, m, data);
+  if (rc) return -rc;
+  *bid = m.Bid; *vuid = m.Vuid; *crc = m.Crc;
+  std::memcpy(out, data.data(), data.size());
+  return (long long)data.size();
+}
+
 }  // extern "C"

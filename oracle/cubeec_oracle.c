@@ -456,3 +456,30 @@ int64_t oracle_crc32block_decode(const uint8_t* src, int64_t total, int64_t bloc
 int64_t oracle_shard_phys_size(int64_t shard_size) {
   return 32 + oracle_crc32block_encode_size(shard_size, 64 * 1024) + 8;
 }
+
+/* ------------------------------------------------------------------------ */
+/* On-disk shard image written by blobnode (BS/blobnode/core/storage/datafile.go:304-408 with     */
+/* core.Shard.WriterHeader / WriterFooter, BS/blobnode/core/shard.go:241-274):                    */
+/*   header(32) = crc32(header[4:32]) BE | magic ab cd ef cc | bid BE64 | vuid BE64 | size BE32 | 0 */
+/*   body       = crc32block framing of the shard data (64 KiB blocks)                             */
+/*   footer(8)  = magic cc ef cd ab | crc32-IEEE(shard data) BE                                    */
+/* ------------------------------------------------------------------------ */
+static void put_be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+static void put_be64(uint8_t* p, uint64_t v) { put_be32(p, (uint32_t)(v >> 32)); put_be32(p + 4, (uint32_t)v); }
+
+int64_t oracle_shard_image(uint64_t bid, uint64_t vuid, const uint8_t* data, uint32_t size, uint8_t* out, uint32_t* crc_out) {
+  static const uint8_t hmagic[4] = {0xab, 0xcd, 0xef, 0xcc}, fmagic[4] = {0xcc, 0xef, 0xcd, 0xab};
+  memcpy(out + 4, hmagic, 4);
+  put_be64(out + 8, bid);
+  put_be64(out + 16, vuid);
+  put_be32(out + 24, size);
+  put_be32(out + 28, 0);
+  put_be32(out, oracle_crc32(ORACLE_CRC_IEEE, 0, out + 4, 28));
+  int64_t body = oracle_crc32block_encode(data, size, 64 * 1024, out + 32);
+  if (body < 0) return -1;
+  uint32_t crc = oracle_crc32(ORACLE_CRC_IEEE, 0, data, size);
+  memcpy(out + 32 + body, fmagic, 4);
+  put_be32(out + 32 + body + 4, crc);
+  if (crc_out) *crc_out = crc;
+  return 32 + body + 8;
+}

@@ -95,6 +95,13 @@ int oracle_rs_encode_batch_simd(const oracle_rs_t*, uint8_t* base, size_t shard_
 int oracle_rs_reconstruct_batch_simd(const oracle_rs_t*, uint8_t* base, size_t shard_len, size_t shard_pitch,
                                      size_t stripe_pitch, size_t n_stripes,
                                      const uint8_t* present /* n_stripes*(k+m) */, int threads);
+/* same, `repeat` passes inside one call (thread start-up amortised; used when timing) */
+int oracle_rs_encode_batch_simd_rep(const oracle_rs_t*, uint8_t* base, size_t shard_len, size_t shard_pitch,
+                                    size_t stripe_pitch, size_t n_stripes, int threads, int with_crc,
+                                    uint32_t* crc_out, size_t repeat);
+int oracle_rs_reconstruct_batch_simd_rep(const oracle_rs_t*, uint8_t* base, size_t shard_len, size_t shard_pitch,
+                                         size_t stripe_pitch, size_t n_stripes, const uint8_t* present, int threads,
+                                         size_t repeat);
 const char* oracle_simd_kind(const oracle_rs_t*);   /* "gfni" | "avx2" | "scalar" */
 int oracle_online_cores(void);
 
@@ -118,6 +125,9 @@ int64_t oracle_crc32block_decode_size(int64_t total, int64_t block_len);
 int64_t oracle_crc32block_encode(const uint8_t* src, int64_t n, int64_t block_len, uint8_t* dst);
 /* Verify + strip; returns payload bytes or -1 on the first mismatched block. */
 int64_t oracle_crc32block_decode(const uint8_t* src, int64_t total, int64_t block_len, uint8_t* dst);
+/* The on-disk image datafile.Write produces for one shard (header | framed body | footer); `out` must
+ * hold oracle_shard_phys_size(size) bytes.  Returns bytes written, -1 on error. */
+int64_t oracle_shard_image(uint64_t bid, uint64_t vuid, const uint8_t* data, uint32_t size, uint8_t* out, uint32_t* crc_out);
 /* core.Alignphysize (BS/blobnode/core/shard.go:419-422). */
 int64_t oracle_shard_phys_size(int64_t shard_size);
 

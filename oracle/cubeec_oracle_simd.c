@@ -60,17 +60,48 @@ static void code_scalar(const uint8_t* rows, int nin, int nout, const uint8_t* c
     }
 }
 
-/* AVX2 nibble-table kernel, up to 4 outputs per pass, 64 bytes per iteration. */
+/* AVX2 nibble-table kernel, NR (<= 4) outputs per pass, 64 bytes per iteration, accumulators in
+ * registers (the shape of klauspost's mulAvxTwo_KxM_64 kernels). */
+#define DEF_AVX2_PASS(NR)                                                                                     \
+  __attribute__((target("avx2"))) static void avx2_pass_##NR(const __m256i* tlo, const __m256i* thi, int nin,  \
+                                                             const uint8_t* const* in, uint8_t* const* out,    \
+                                                             size_t vec_bytes) {                               \
+    const __m256i mask = _mm256_set1_epi8(0x0f);                                                               \
+    for (size_t i = 0; i < vec_bytes; i += 64) {                                                               \
+      __m256i a0[NR], a1[NR];                                                                                  \
+      for (int r = 0; r < NR; r++) { a0[r] = _mm256_setzero_si256(); a1[r] = _mm256_setzero_si256(); }         \
+      for (int c = 0; c < nin; c++) {                                                                          \
+        const __m256i d0 = _mm256_loadu_si256((const __m256i*)(in[c] + i));                                    \
+        const __m256i d1 = _mm256_loadu_si256((const __m256i*)(in[c] + i + 32));                               \
+        const __m256i l0 = _mm256_and_si256(d0, mask), h0 = _mm256_and_si256(_mm256_srli_epi64(d0, 4), mask);  \
+        const __m256i l1 = _mm256_and_si256(d1, mask), h1 = _mm256_and_si256(_mm256_srli_epi64(d1, 4), mask);  \
+        for (int r = 0; r < NR; r++) {                                                                         \
+          const __m256i tl = tlo[c * 4 + r], th = thi[c * 4 + r];                                              \
+          a0[r] = _mm256_xor_si256(a0[r], _mm256_xor_si256(_mm256_shuffle_epi8(tl, l0), _mm256_shuffle_epi8(th, h0))); \
+          a1[r] = _mm256_xor_si256(a1[r], _mm256_xor_si256(_mm256_shuffle_epi8(tl, l1), _mm256_shuffle_epi8(th, h1))); \
+        }                                                                                                      \
+      }                                                                                                        \
+      for (int r = 0; r < NR; r++) {                                                                           \
+        _mm256_storeu_si256((__m256i*)(out[r] + i), a0[r]);                                                    \
+        _mm256_storeu_si256((__m256i*)(out[r] + i + 32), a1[r]);                                               \
+      }                                                                                                        \
+    }                                                                                                          \
+  }
+DEF_AVX2_PASS(1)
+DEF_AVX2_PASS(2)
+DEF_AVX2_PASS(3)
+DEF_AVX2_PASS(4)
+
 __attribute__((target("avx2")))
 static void code_avx2(const uint8_t* rows, int nin, int nout, const uint8_t* const* in,
                       uint8_t* const* out, size_t bytes) {
   const uint8_t* mul = oracle_gf_mul_table();
   size_t vec_bytes = bytes & ~(size_t)63;
+  __m256i* tlo = (__m256i*)aligned_alloc(32, (size_t)nin * 4 * 32);
+  __m256i* thi = (__m256i*)aligned_alloc(32, (size_t)nin * 4 * 32);
   for (int r0 = 0; r0 < nout; r0 += 4) {
     int nr = nout - r0 < 4 ? nout - r0 : 4;
     /* tables: [c][r][lo|hi] 16 bytes each, broadcast to both lanes */
-    __m256i* tlo = (__m256i*)aligned_alloc(32, (size_t)nin * 4 * 32);
-    __m256i* thi = (__m256i*)aligned_alloc(32, (size_t)nin * 4 * 32);
     for (int c = 0; c < nin; c++)
       for (int r = 0; r < nr; r++) {
         uint8_t lo[16], hi[16];
@@ -79,29 +110,15 @@ static void code_avx2(const uint8_t* rows, int nin, int nout, const uint8_t* con
         tlo[c * 4 + r] = _mm256_broadcastsi128_si256(_mm_loadu_si128((const __m128i*)lo));
         thi[c * 4 + r] = _mm256_broadcastsi128_si256(_mm_loadu_si128((const __m128i*)hi));
       }
-    const __m256i mask = _mm256_set1_epi8(0x0f);
-    for (size_t i = 0; i < vec_bytes; i += 64) {
-      __m256i a0[4], a1[4];
-      for (int r = 0; r < nr; r++) { a0[r] = _mm256_setzero_si256(); a1[r] = _mm256_setzero_si256(); }
-      for (int c = 0; c < nin; c++) {
-        __m256i d0 = _mm256_loadu_si256((const __m256i*)(in[c] + i));
-        __m256i d1 = _mm256_loadu_si256((const __m256i*)(in[c] + i + 32));
-        __m256i l0 = _mm256_and_si256(d0, mask), h0 = _mm256_and_si256(_mm256_srli_epi64(d0, 4), mask);
-        __m256i l1 = _mm256_and_si256(d1, mask), h1 = _mm256_and_si256(_mm256_srli_epi64(d1, 4), mask);
-        for (int r = 0; r < nr; r++) {
-          __m256i tl = tlo[c * 4 + r], th = thi[c * 4 + r];
-          a0[r] = _mm256_xor_si256(a0[r], _mm256_xor_si256(_mm256_shuffle_epi8(tl, l0), _mm256_shuffle_epi8(th, h0)));
-          a1[r] = _mm256_xor_si256(a1[r], _mm256_xor_si256(_mm256_shuffle_epi8(tl, l1), _mm256_shuffle_epi8(th, h1)));
-        }
-      }
-      for (int r = 0; r < nr; r++) {
-        _mm256_storeu_si256((__m256i*)(out[r0 + r] + i), a0[r]);
-        _mm256_storeu_si256((__m256i*)(out[r0 + r] + i + 32), a1[r]);
-      }
+    switch (nr) {
+      case 1: avx2_pass_1(tlo, thi, nin, in, out + r0, vec_bytes); break;
+      case 2: avx2_pass_2(tlo, thi, nin, in, out + r0, vec_bytes); break;
+      case 3: avx2_pass_3(tlo, thi, nin, in, out + r0, vec_bytes); break;
+      default: avx2_pass_4(tlo, thi, nin, in, out + r0, vec_bytes); break;
     }
-    free(tlo);
-    free(thi);
   }
+  free(tlo);
+  free(thi);
   if (vec_bytes < bytes) code_scalar(rows, nin, nout, in, out, vec_bytes, bytes);
 }
 
@@ -226,6 +243,7 @@ typedef struct {
   const uint8_t* present; /* reconstruct only */
   int with_crc;
   uint32_t* crc_out;
+  size_t repeat; /* passes over the batch inside one call (amortises thread start-up when timing) */
   atomic_size_t next;
   atomic_int err;
 } batch_t;
@@ -236,7 +254,8 @@ static void* encode_worker(void* arg) {
   const uint8_t* rows = oracle_rs_matrix(b->rs) + (size_t)k * k;
   for (;;) {
     size_t s = atomic_fetch_add(&b->next, 1);
-    if (s >= b->n_stripes) break;
+    if (s >= b->n_stripes * b->repeat) break;
+    s %= b->n_stripes;
     uint8_t* sp = b->base + s * b->stripe_pitch;
     const uint8_t* in[256];
     uint8_t* out[256];
@@ -258,7 +277,8 @@ static void* reconstruct_worker(void* arg) {
   uint8_t* rows = (uint8_t*)malloc((size_t)n * k);
   for (;;) {
     size_t s = atomic_fetch_add(&b->next, 1);
-    if (s >= b->n_stripes) break;
+    if (s >= b->n_stripes * b->repeat) break;
+    s %= b->n_stripes;
     uint8_t* sp = b->base + s * b->stripe_pitch;
     const uint8_t* pres = b->present + s * (size_t)n;
     int valid[256];
@@ -284,7 +304,8 @@ static void* reconstruct_worker(void* arg) {
 
 static int run_batch(batch_t* b, int threads, void* (*fn)(void*)) {
   if (threads <= 0) threads = oracle_online_cores();
-  if ((size_t)threads > b->n_stripes) threads = (int)(b->n_stripes ? b->n_stripes : 1);
+  if (b->repeat == 0) b->repeat = 1;
+  if ((size_t)threads > b->n_stripes * b->repeat) threads = (int)(b->n_stripes ? b->n_stripes * b->repeat : 1);
   oracle_gf_mul_table(); /* build tables before the threads race to */
   oracle_crc32(0, 0, "", 0);
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
@@ -314,6 +335,30 @@ int oracle_rs_reconstruct_batch_simd(const oracle_rs_t* rs, uint8_t* base, size_
   memset(&b, 0, sizeof(b));
   b.rs = rs; b.base = base; b.shard_len = shard_len; b.shard_pitch = shard_pitch;
   b.stripe_pitch = stripe_pitch; b.n_stripes = n_stripes; b.present = present;
+  atomic_init(&b.next, 0); atomic_init(&b.err, 0);
+  return run_batch(&b, threads, reconstruct_worker);
+}
+
+/* Timing variants: `repeat` passes over the batch inside one call. */
+int oracle_rs_encode_batch_simd_rep(const oracle_rs_t* rs, uint8_t* base, size_t shard_len, size_t shard_pitch,
+                                    size_t stripe_pitch, size_t n_stripes, int threads, int with_crc, uint32_t* crc_out,
+                                    size_t repeat) {
+  if (!rs || !base || shard_len == 0) return ORACLE_ERR_INVALID_ARG;
+  batch_t b;
+  memset(&b, 0, sizeof(b));
+  b.rs = rs; b.base = base; b.shard_len = shard_len; b.shard_pitch = shard_pitch;
+  b.stripe_pitch = stripe_pitch; b.n_stripes = n_stripes; b.with_crc = with_crc; b.crc_out = crc_out; b.repeat = repeat;
+  atomic_init(&b.next, 0); atomic_init(&b.err, 0);
+  return run_batch(&b, threads, encode_worker);
+}
+int oracle_rs_reconstruct_batch_simd_rep(const oracle_rs_t* rs, uint8_t* base, size_t shard_len, size_t shard_pitch,
+                                         size_t stripe_pitch, size_t n_stripes, const uint8_t* present, int threads,
+                                         size_t repeat) {
+  if (!rs || !base || !present || shard_len == 0) return ORACLE_ERR_INVALID_ARG;
+  batch_t b;
+  memset(&b, 0, sizeof(b));
+  b.rs = rs; b.base = base; b.shard_len = shard_len; b.shard_pitch = shard_pitch;
+  b.stripe_pitch = stripe_pitch; b.n_stripes = n_stripes; b.present = present; b.repeat = repeat;
   atomic_init(&b.next, 0); atomic_init(&b.err, 0);
   return run_batch(&b, threads, reconstruct_worker);
 }

@@ -64,6 +64,10 @@ def lib() -> C.CDLL:
                                                   C.c_int, C.c_int, vp]
         L.oracle_rs_reconstruct_batch_simd.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
                                                        vp, C.c_int]
+        L.oracle_rs_encode_batch_simd_rep.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                      C.c_int, C.c_int, vp, C.c_size_t]
+        L.oracle_rs_reconstruct_batch_simd_rep.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                           vp, C.c_int, C.c_size_t]
         L.oracle_simd_kind.argtypes = [vp]
         L.oracle_simd_kind.restype = C.c_char_p
         L.oracle_split_shard_size.argtypes = [C.c_size_t, C.c_int]
@@ -82,6 +86,8 @@ def lib() -> C.CDLL:
         L.oracle_crc32block_encode.restype = C.c_int64
         L.oracle_crc32block_decode.argtypes = [vp, C.c_int64, C.c_int64, vp]
         L.oracle_crc32block_decode.restype = C.c_int64
+        L.oracle_shard_image.argtypes = [C.c_uint64, C.c_uint64, vp, C.c_uint32, vp, C.POINTER(C.c_uint32)]
+        L.oracle_shard_image.restype = C.c_int64
         L.oracle_shard_phys_size.argtypes = [C.c_int64]
         L.oracle_shard_phys_size.restype = C.c_int64
         _lib = L
@@ -217,17 +223,17 @@ class RS:
         return list(valid), rows
 
     def encode_batch_simd(self, buf: np.ndarray, shard_len, shard_pitch, stripe_pitch, n_stripes,
-                          threads=0, crc_out=None):
-        rc = lib().oracle_rs_encode_batch_simd(self._h, _ptr(buf), shard_len, shard_pitch, stripe_pitch,
-                                               n_stripes, threads, int(crc_out is not None),
-                                               _ptr(crc_out) if crc_out is not None else None)
+                          threads=0, crc_out=None, repeat=1):
+        rc = lib().oracle_rs_encode_batch_simd_rep(self._h, _ptr(buf), shard_len, shard_pitch, stripe_pitch,
+                                                   n_stripes, threads, int(crc_out is not None),
+                                                   _ptr(crc_out) if crc_out is not None else None, repeat)
         if rc:
             raise OracleError(rc)
 
-    def reconstruct_batch_simd(self, buf, shard_len, shard_pitch, stripe_pitch, n_stripes, present, threads=0):
+    def reconstruct_batch_simd(self, buf, shard_len, shard_pitch, stripe_pitch, n_stripes, present, threads=0, repeat=1):
         present = np.ascontiguousarray(present, dtype=np.uint8)
-        rc = lib().oracle_rs_reconstruct_batch_simd(self._h, _ptr(buf), shard_len, shard_pitch, stripe_pitch,
-                                                    n_stripes, _ptr(present), threads)
+        rc = lib().oracle_rs_reconstruct_batch_simd_rep(self._h, _ptr(buf), shard_len, shard_pitch, stripe_pitch,
+                                                        n_stripes, _ptr(present), threads, repeat)
         if rc:
             raise OracleError(rc)
 
@@ -267,3 +273,13 @@ def crc32block_decode(src: bytes, block_len: int = 65536):
     out = np.zeros(max(len(a), 1), dtype=np.uint8)
     w = lib().oracle_crc32block_decode(_ptr(a) if a.size else None, a.size, block_len, _ptr(out))
     return None if w < 0 else out[:w].tobytes()
+
+
+def shard_image(bid: int, vuid: int, data: bytes):
+    """(image bytes, shard crc) as blobnode's datafile.Write lays a shard out on disk."""
+    a = np.frombuffer(data, dtype=np.uint8)
+    out = np.zeros(int(lib().oracle_shard_phys_size(len(a))), dtype=np.uint8)
+    crc = C.c_uint32(0)
+    n = lib().oracle_shard_image(bid, vuid, _ptr(a) if a.size else None, a.size, _ptr(out), C.byref(crc))
+    assert n == out.size
+    return out.tobytes(), int(crc.value)

@@ -254,3 +254,41 @@ def test_crc32block_round_trip(oracle):
         with pytest.raises(cm.EcError) as e:
             cm.BlockDecode(bytes(bad))
         assert e.value.name == "ErrMismatchedCrc"
+
+
+def test_shard_image_layout_cpu(oracle):
+    """datafile_test.go:175-260: a 9-byte shard occupies 32+(9+4)+8 bytes, page-aligned to 4096; 32 KiB -> 4096+32768."""
+    assert cm.Alignphysize(9) == 53 and cm.AlignSize(4096 + 53, 4096) == 8192
+    assert cm.AlignSize(65536 + cm.Alignphysize(32768), 4096) == 65536 + 4096 + 32768
+    img, crc = oracle.shard_image(1024, 10, b"test data")
+    assert crc == 3540561586 and len(img) == 53
+    assert img[4:8] == bytes([0xab, 0xcd, 0xef, 0xcc]) and img[-8:-4] == bytes([0xcc, 0xef, 0xcd, 0xab])
+    assert int.from_bytes(img[8:16], "big") == 1024 and int.from_bytes(img[16:24], "big") == 10
+    assert int.from_bytes(img[24:28], "big") == 9 and int.from_bytes(img[-4:], "big") == 3540561586
+    assert int.from_bytes(img[:4], "big") == zlib.crc32(img[4:32])
+
+
+@pytest.mark.gpu
+def test_shard_write_read_matches_oracle(oracle):
+    """blobnode shard write (datafile.Write) with GPU CRCs == the oracle's restatement, byte for byte;
+    read-back verifies; the reference's golden CRCs hold (datafile_test.go:198-396)."""
+    rng = np.random.default_rng(6)
+    cases = [b"test data", bytes(ord("0") + i % 10 for i in range(32768))]
+    cases += [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (1, 65531, 65532, 65533, 349526, 1 << 20)]
+    golden = {0: 3540561586, 1: 629387998}
+    for i, data in enumerate(cases):
+        img, crc = cm.WriteShard(1024 + i, 10, data)
+        want_img, want_crc = oracle.shard_image(1024 + i, 10, data)
+        assert img == want_img and crc == want_crc == zlib.crc32(data)
+        if i in golden:
+            assert crc == golden[i]
+        bid, vuid, rcrc, back = cm.ReadShard(img)
+        assert (bid, vuid, rcrc, back) == (1024 + i, 10, crc, data)
+        for pos, err in ((5, "ErrShardHeaderMagic"), (20, "ErrShardHeaderCrc"), (40, "ErrMismatchedCrc"), (len(img) - 1, "ErrShardCrc")):
+            if pos >= len(img) - 8 and pos < len(img) - 4:
+                continue
+            bad = bytearray(img)
+            bad[pos] ^= 0x10
+            with pytest.raises(cm.EcError) as e:
+                cm.ReadShard(bytes(bad))
+            assert e.value.name == err, (i, pos)
