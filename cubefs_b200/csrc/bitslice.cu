@@ -129,10 +129,11 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
   uint32_t* fold_s = reinterpret_cast<uint32_t*>(smem + 64);                       // [4][256][kBsFoldCopies]
   uint32_t* kth_s = fold_s + 4 * 256 * kBsFoldCopies;                              // [NT]
   uint32_t* red_s = kth_s + NT;                                                    // [(K+M)][NW]
+  uint32_t* red2_s = red_s + (K + M) * NW;                                         // packed mode: [kBsPackedMaxStripes][(K+M)]
   const uint32_t base_addr = smem_addr(smem);
   uint32_t tab_addr = 0;   // shared address of the slice image
   if (CRC) {
-    tab_addr = (base_addr + (uint32_t)(64 + 4 * 256 * kBsFoldCopies * 4 + NT * 4 + (K + M) * NW * 4) + 65535u) & ~65535u;
+    tab_addr = (base_addr + (uint32_t)(64 + 4 * 256 * kBsFoldCopies * 4 + NT * 4 + (K + M) * NW * 4 + kBsPackedMaxStripes * (K + M) * 4) + 65535u) & ~65535u;
     uint8_t* tab_ptr = smem + (tab_addr - base_addr);
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
@@ -199,6 +200,120 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
 #pragma unroll
   for (int i = 0; i < K + M; i++) crc_u[i] = 0;
 
+  // (an explicit prefetch.global.L2 of the next column group was measured: 30 % slower -- not used)
+  // one 32-byte group of every shard.  FULL = the whole tile lies inside [0, shard_len): no
+  // predicates, no tail masks (every tile but the last of a shard).
+  auto group = [&](auto full_tag, uint8_t* sbase, const size_t col) {
+    constexpr bool FULL = decltype(full_tag)::value;
+    const bool live = FULL || col < p.shard_len;
+    const int tail = (!FULL && live && col + 32 > p.shard_len) ? (int)(p.shard_len - col) : 0;
+    uint32_t msk[8];
+    if (!FULL) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int rem = tail - 4 * i;
+        msk[i] = (tail == 0 || rem >= 4) ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
+      }
+    }
+    uint32_t acc[8 * M];
+#pragma unroll
+    for (int i = 0; i < 8 * M; i++) acc[i] = 0;
+    // Look-ahead ring: DEPTH 256-bit loads per thread in flight ahead of the shard being coded.
+    // The fused-CRC variant is ALU/issue bound and out of registers (DEPTH 1); the plain variant is
+    // latency bound and uses its spare registers for a deep ring.
+    constexpr int DEPTH = CRC ? 1 : 4;
+    uint32_t ring[DEPTH + 1][8];
+#pragma unroll
+    for (int b = 0; b <= DEPTH; b++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) ring[b][i] = 0;
+    const uint8_t* src = sbase + col;
+    auto shard = [&](const int c, uint32_t (&w)[8]) {
+      if (!FULL) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] &= msk[i];
+      }
+      if (CRC) {
+        uint32_t u = crc_u[c];
+#pragma unroll
+        for (int i = 0; i < 8; i++) u = slice4(u ^ w[i]);
+        crc_u[c] = u;
+      }
+      bit_transpose8(w);
+      ApplyAt<Net, 0, K>::run(c, w, acc);   // c is a compile-time constant after unrolling
+    };
+#pragma unroll
+    for (int c = 0; c < DEPTH && c < K; c++)
+      if (live) ldg256(src + (size_t)c * p.shard_pitch, ring[c % (DEPTH + 1)]);
+#pragma unroll
+    for (int c = 0; c < K; c++) {
+      if (c + DEPTH < K && live) ldg256(src + (size_t)(c + DEPTH) * p.shard_pitch, ring[(c + DEPTH) % (DEPTH + 1)]);
+      shard(c, ring[c % (DEPTH + 1)]);
+    }
+#pragma unroll
+    for (int r = 0; r < M; r++) {
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) o[i] = acc[r * 8 + i];
+      bit_transpose8(o);
+      if (live) stg256(sbase + (size_t)(K + r) * p.shard_pitch + col, o);
+      if (CRC) {
+        uint32_t u = crc_u[K + r];
+#pragma unroll
+        for (int i = 0; i < 8; i++) u = slice4(u ^ o[i]);
+        crc_u[K + r] = u;
+      }
+    }
+  };
+
+
+  if (p.packed_pps) {
+    // ---- packed mode: shards shorter than a tile.  The (stripe, 64-byte piece) pairs of the whole
+    // batch are laid end to end and a tile takes 512 of them, so small shards (2 KiB is the
+    // production minimum) still fill the CTA.  One piece per thread: no Horner step; the per-thread
+    // CRC remainder is aligned to the end of its own shard and XOR-reduced per stripe.
+    const uint32_t PPS = p.packed_pps;
+    const uint64_t F = (uint64_t)p.n_stripes * PPS;
+    const uint32_t n_tiles = (uint32_t)((F + NT - 1) / NT);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint64_t f = (uint64_t)tile * NT + tid;
+      const bool active = f < F;
+      const uint32_t stripe = active ? (uint32_t)(f / PPS) : 0xFFFFFFFFu;
+      const uint32_t pos = active ? (uint32_t)(f - (uint64_t)stripe * PPS) : 0u;
+      if (active) {
+        uint8_t* sb = p.base + (size_t)stripe * p.stripe_pitch;
+#pragma unroll 1
+        for (int g = 0; g < kBsGroups; g++) group(std::false_type{}, sb, (size_t)pos * kBsPiece + (size_t)g * 32);
+      }
+      if (CRC && p.crc_part) {
+        const uint32_t stripe0 = (uint32_t)(((uint64_t)tile * NT) / PPS);
+        uint64_t last_f = (uint64_t)(tile + 1) * NT - 1;
+        if (last_f >= F) last_f = F - 1;
+        const uint32_t nstr = (uint32_t)(last_f / PPS) - stripe0 + 1;
+        for (uint32_t i = tid; i < nstr * (K + M); i += NT) red2_s[i] = 0;
+        __syncthreads();
+        const uint32_t kt = active ? kth_s[pos + NT - PPS] : 0u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, stripe);
+        const bool leader = active && (lane == __ffs(peers) - 1);
+#pragma unroll
+        for (int q = 0; q < K + M; q++) {
+          uint32_t u = active ? gf32_mul_dev(crc_u[q], kt, p.poly) : 0u;
+          crc_u[q] = 0;
+          u = __reduce_xor_sync(peers, u);
+          if (leader) atomicXor(&red2_s[(stripe - stripe0) * (K + M) + q], u);
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < nstr * (K + M); i += NT) {
+          const uint32_t sj = stripe0 + i / (K + M), q = i % (K + M);
+          const uint32_t segidx = tile - (uint32_t)(((uint64_t)sj * PPS) / NT);   // 0 or 1: a shard spans at most two tiles
+          p.crc_part[((size_t)sj * p.n_slots + q) * 2 + segidx] = red2_s[i];
+        }
+        __syncthreads();
+      }
+    }
+    return;
+  }
+
   const uint32_t n_items = p.n_stripes * p.n_seg;
   const size_t seg_bytes = (size_t)p.tiles_per_seg * kBsTile;
 
@@ -208,72 +323,6 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
     const uint32_t T = (seg == p.n_seg - 1) ? p.tiles_last : p.tiles_per_seg;
     const size_t seg_start = (size_t)seg * seg_bytes;
 
-    // one 32-byte group of every shard.  FULL = the whole tile lies inside [0, shard_len): no
-    // predicates, no tail masks (every tile but the last of a shard).
-    auto group = [&](auto full_tag, const size_t col, const size_t next_col) {
-      constexpr bool FULL = decltype(full_tag)::value;
-      const bool live = FULL || col < p.shard_len;
-      const int tail = (!FULL && live && col + 32 > p.shard_len) ? (int)(p.shard_len - col) : 0;
-      (void)next_col;   // (an explicit prefetch.global.L2 of the next column group was measured: 30 % slower)
-      uint32_t msk[8];
-      if (!FULL) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int rem = tail - 4 * i;
-          msk[i] = (tail == 0 || rem >= 4) ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
-        }
-      }
-      uint32_t acc[8 * M];
-#pragma unroll
-      for (int i = 0; i < 8 * M; i++) acc[i] = 0;
-      // Look-ahead ring: DEPTH 256-bit loads per thread in flight ahead of the shard being coded.
-      // The fused-CRC variant is ALU/issue bound and out of registers (DEPTH 1); the plain variant is
-      // latency bound and uses its spare registers for a deep ring.
-      constexpr int DEPTH = CRC ? 1 : 4;
-      uint32_t ring[DEPTH + 1][8];
-#pragma unroll
-      for (int b = 0; b <= DEPTH; b++)
-#pragma unroll
-        for (int i = 0; i < 8; i++) ring[b][i] = 0;
-      const uint8_t* src = sbase + col;
-      auto shard = [&](const int c, uint32_t (&w)[8]) {
-        if (!FULL) {
-#pragma unroll
-          for (int i = 0; i < 8; i++) w[i] &= msk[i];
-        }
-        if (CRC) {
-          uint32_t u = crc_u[c];
-#pragma unroll
-          for (int i = 0; i < 8; i++) u = slice4(u ^ w[i]);
-          crc_u[c] = u;
-        }
-        bit_transpose8(w);
-        ApplyAt<Net, 0, K>::run(c, w, acc);   // c is a compile-time constant after unrolling
-      };
-#pragma unroll
-      for (int c = 0; c < DEPTH && c < K; c++)
-        if (live) ldg256(src + (size_t)c * p.shard_pitch, ring[c % (DEPTH + 1)]);
-#pragma unroll
-      for (int c = 0; c < K; c++) {
-        if (c + DEPTH < K && live) ldg256(src + (size_t)(c + DEPTH) * p.shard_pitch, ring[(c + DEPTH) % (DEPTH + 1)]);
-        shard(c, ring[c % (DEPTH + 1)]);
-      }
-#pragma unroll
-      for (int r = 0; r < M; r++) {
-        uint32_t o[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) o[i] = acc[r * 8 + i];
-        bit_transpose8(o);
-        if (live) stg256(sbase + (size_t)(K + r) * p.shard_pitch + col, o);
-        if (CRC) {
-          uint32_t u = crc_u[K + r];
-#pragma unroll
-          for (int i = 0; i < 8; i++) u = slice4(u ^ o[i]);
-          crc_u[K + r] = u;
-        }
-      }
-    };
-
     for (uint32_t t = 0; t < T; t++) {
       if (CRC) {
         // Horner step: skip the gap between the end of this thread's previous piece and this one
@@ -282,15 +331,12 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
       }
       const size_t tile_start = seg_start + (size_t)t * kBsTile;
       const size_t col0 = tile_start + (size_t)tid * kBsPiece;
-      // next group of this thread: the other half of its 64-byte piece, then the piece of the next tile
       if (tile_start + kBsTile <= p.shard_len) {
 #pragma unroll 1
-        for (int g = 0; g < kBsGroups; g++)
-          group(std::true_type{}, col0 + (size_t)g * 32, g + 1 < kBsGroups ? col0 + (size_t)(g + 1) * 32 : (t + 1 < T ? col0 + kBsTile : (size_t)-1));
+        for (int g = 0; g < kBsGroups; g++) group(std::true_type{}, sbase, col0 + (size_t)g * 32);
       } else {
 #pragma unroll 1
-        for (int g = 0; g < kBsGroups; g++)
-          group(std::false_type{}, col0 + (size_t)g * 32, g + 1 < kBsGroups ? col0 + (size_t)(g + 1) * 32 : (t + 1 < T ? col0 + kBsTile : (size_t)-1));
+        for (int g = 0; g < kBsGroups; g++) group(std::false_type{}, sbase, col0 + (size_t)g * 32);
       }
     }
 

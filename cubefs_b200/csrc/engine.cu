@@ -394,6 +394,7 @@ struct Geometry {
   uint32_t n_seg, tiles_per_seg, tiles_last;
   int grid;
   uint32_t tile;   // bytes of a shard per tile
+  uint32_t packed_pps = 0;   // bit-sliced kernel packed mode: 64-byte pieces per shard (see BsParams)
 };
 
 Geometry pick_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes, bool per_stripe_patterns,
@@ -475,9 +476,15 @@ int finalize_crc(DevCtx& c, cudaStream_t stream, const uint32_t* d_crc_part, siz
   f.n_seg = gm.n_seg;
   const int64_t seg_bytes = (int64_t)gm.tiles_per_seg * gm.tile;
   const int64_t last_bytes = (int64_t)gm.tiles_last * gm.tile;
-  const int64_t virt = (int64_t)(gm.n_seg - 1) * seg_bytes + last_bytes;
+  int64_t virt = (int64_t)(gm.n_seg - 1) * seg_bytes + last_bytes;
   f.x_full = P.shift_bytes_const(seg_bytes);
   f.x_last = P.shift_bytes_const(last_bytes);
+  if (gm.packed_pps) {
+    // packed mode: the (at most two) partial remainders of a shard are already aligned to the end of
+    // the shard's last 64-byte piece, so they are simply XORed (multiplier x^0)
+    f.x_full = f.x_last = 0x80000000u;
+    virt = (int64_t)gm.packed_pps * kBsPiece;
+  }
   f.fix = P.shift_bytes_const(-(virt - (int64_t)shard_len));
   f.init_term = P.mul(0xFFFFFFFFu, P.shift_bytes_const((int64_t)shard_len));
   f.poly = P.poly;
@@ -526,7 +533,7 @@ size_t crc_part_bytes(const DevCtx& c, size_t shard_len, size_t n_stripes, int n
   // upper bound over both kernels' geometries
   const Geometry g1 = pick_geometry(c, shard_len, n_stripes, false);
   const Geometry g2 = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
-  return n_stripes * (size_t)n_slots * std::max(g1.n_seg, g2.n_seg) * sizeof(uint32_t);
+  return n_stripes * (size_t)n_slots * std::max<uint32_t>(std::max(g1.n_seg, g2.n_seg), 2u) * sizeof(uint32_t);
 }
 
 // The bit-sliced kernel needs 32-byte columns: base and pitches 32-aligned, room for whole groups.
@@ -547,12 +554,22 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
   const bool want_crc = mode == 0 && d_crc_out;
   if (mode == 0 && h->bs_ok && g_force_kernel.load() != 1 && bs_layout_ok(d_base, shard_len, shard_pitch, stripe_pitch)) {
     // hot path: bit-sliced XOR-network kernel (bitslice.cu)
-    const Geometry gm = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
+    Geometry gm = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
+    // shards shorter than a tile: packed mode (pieces of many stripes share a tile)
+    const uint32_t pps = (uint32_t)((shard_len + kBsPiece - 1) / kBsPiece);
+    const bool packed = pps < (uint32_t)kBsThreads && pps >= 8;
+    if (packed) {
+      const uint64_t tiles = ((uint64_t)n_stripes * pps + kBsThreads - 1) / kBsThreads;
+      gm.n_seg = 2;               // a shard's pieces fall into at most two tiles
+      gm.packed_pps = pps;
+      gm.grid = (int)std::min<uint64_t>(tiles, (uint64_t)c.sm_count);
+    }
     bool own = false;
     if (want_crc && !d_part) {
       CU(cudaMallocAsync(&d_part, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
       own = true;
     }
+    if (want_crc && packed) CU(cudaMemsetAsync(d_part, 0, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
     BsParams bp;
     std::memset(&bp, 0, sizeof(bp));
     bp.base = d_base;
@@ -571,6 +588,7 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
     bp.kthread = c.d_bs_kthread[pi];
     bp.poly = g.poly[pi].poly;
     bp.k65536 = 65536u;
+    bp.packed_pps = gm.packed_pps;
     CU(launch_bs(h->k, h->m, bp, want_crc, gm.grid, stream));
     g_launches++;
     t_last_kernel = want_crc ? "rs_bs_kernel<crc>" : "rs_bs_kernel";

@@ -113,6 +113,7 @@ constexpr int kBsGroups = 2;                                  // 32-byte groups 
 constexpr int kBsPiece = 32 * kBsGroups;                      // contiguous bytes per thread per tile
 constexpr int kBsTile = kBsThreads * kBsPiece;                // bytes of every shard per tile
 constexpr int kBsFoldCopies = 4;
+constexpr int kBsPackedMaxStripes = 72;                       // stripes a packed tile can touch (pieces/shard >= 8)
 constexpr size_t kBsSliceImageBytes = 2 * 65536;
 constexpr size_t kBsMiscBytes = 4 * 256 * kBsFoldCopies * 4 + kBsThreads * 4 + 64;
 constexpr size_t kBsSmemBytes = 65536 + kBsSliceImageBytes + 1024;
@@ -129,6 +130,7 @@ struct BsParams {
   const uint32_t* kthread;            // global: [kBsThreads] x^(8*(tile - piece*(tid+1)))
   uint32_t poly;
   uint32_t k65536;                    // = 65536, opaque to the compiler (see slice4 in bitslice.cu)
+  uint32_t packed_pps;                // 0 = one shard spans >= 1 tile; else 64-byte pieces per shard (< kBsThreads): packed mode
 };
 
 

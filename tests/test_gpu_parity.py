@@ -423,3 +423,41 @@ def test_device_reconstruct_syndrome_kernel(cb, oracle, km):
     with pytest.raises(cb.CubeecError) as e:
         eng.dev_reconstruct(dev.data_ptr(), S, P, n * P, 1, present2)
     assert e.value.name == "ErrTooFewShards"
+
+
+@pytest.mark.parametrize("km", [(12, 4), (6, 3), (4, 2)])
+def test_small_shards_packed_mode(cb, oracle, km):
+    """Shards shorter than a tile (2 KiB is the production MinShardSize): the bit-sliced kernel packs the
+    pieces of many stripes into one tile.  Parity and CRCs must still match the oracle for every size,
+    including sizes that are not multiples of 64 and batches whose last tile is partly empty."""
+    import torch
+    k, m = km
+    n = k + m
+    rng = np.random.default_rng(k + 100 * m)
+    for S, ns in ((2048, 300), (4096, 77), (2048 + 6, 41), (511, 9), (16384, 33), (32767, 5), (20000, 130), (640, 1000)):
+        P = (S + 127) // 128 * 128
+        host = rng.integers(0, 256, (ns, n, P), dtype=np.uint8)
+        dev = torch.from_numpy(host).cuda()
+        dcrc = torch.zeros(ns * n, dtype=torch.int32, device="cuda")
+        eng = cb.RSEngine(k, m)
+        eng.dev_encode(dev.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr())
+        assert cb.last_kernel() == "rs_bs_kernel<crc>"
+        torch.cuda.synchronize()
+        out = dev.cpu().numpy()
+        crc = dcrc.cpu().numpy().view(np.uint32).reshape(ns, n)
+        dev2 = torch.from_numpy(host).cuda()
+        eng.dev_encode(dev2.data_ptr(), S, P, n * P, ns)          # without CRC
+        torch.cuda.synchronize()
+        assert torch.equal(dev2[:, :, :S].cpu(), torch.from_numpy(out[:, :, :S]))
+        ora = oracle.RS(k, m)
+        for s in list(range(min(ns, 6))) + [ns // 2, ns - 1]:
+            sh = [host[s, i, :S].copy() for i in range(n)]
+            ora.encode(sh)
+            for i in range(n):
+                assert (out[s, i, :S] == sh[i]).all(), (km, S, s, i)
+                assert crc[s, i] == zlib.crc32(sh[i].tobytes()), (km, S, s, i)
+        # all stripes: parity by linear algebra on the whole batch (oracle SIMD path) and CRC of every shard
+        want = host[:, :, :S].copy()
+        ora.encode_batch_simd(want, S, S, n * S, ns)
+        assert (out[:, :, :S] == want).all(), (km, S)
+        assert all(crc[s, i] == zlib.crc32(want[s, i].tobytes()) for s in range(ns) for i in range(n)), (km, S)
