@@ -117,7 +117,7 @@ struct ApplyAt<Net, K, K> {
 
 }  // namespace
 
-template <int K, int M, bool CRC>
+template <int K, int M, bool CRC, bool PACKED>
 __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) {
   using Net = BsNet<K, M>;
   constexpr int NT = kBsThreads, NW = NT / 32;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
   };
 
 
-  if (p.packed_pps) {
+  if constexpr (PACKED) {
     // ---- packed mode: shards shorter than a tile.  The (stripe, 64-byte piece) pairs of the whole
     // batch are laid end to end and a tile takes 512 of them, so small shards (2 KiB is the
     // production minimum) still fill the CTA.  One piece per thread: no Horner step; the per-thread
@@ -311,8 +311,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
         __syncthreads();
       }
     }
-    return;
-  }
+  } else {
 
   const uint32_t n_items = p.n_stripes * p.n_seg;
   const size_t seg_bytes = (size_t)p.tiles_per_seg * kBsTile;
@@ -359,6 +358,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
       __syncthreads();
     }
   }
+  }   // !PACKED
 }
 
 
@@ -581,11 +581,16 @@ static cudaError_t launch_cfg(const BsParams& p, bool crc, int grid, cudaStream_
   static bool configured = false;   // per process; attribute is per device function, set for every device lazily
   cudaError_t e;
   (void)configured;
-  if ((e = cudaFuncSetAttribute(rs_bs_kernel<K, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)kBsSmemBytes)) != cudaSuccess)
-    return e;
-  if (crc) rs_bs_kernel<K, M, true><<<grid, kBsThreads, kBsSmemBytes, st>>>(p);
-  else rs_bs_kernel<K, M, false><<<grid, kBsThreads, 4096, st>>>(p);
+  const bool packed = p.packed_pps != 0;
+  if (crc) {
+    auto kern = packed ? rs_bs_kernel<K, M, true, true> : rs_bs_kernel<K, M, true, false>;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsSmemBytes)) != cudaSuccess) return e;
+    kern<<<grid, kBsThreads, kBsSmemBytes, st>>>(p);
+  } else if (packed) {
+    rs_bs_kernel<K, M, false, true><<<grid, kBsThreads, 4096, st>>>(p);
+  } else {
+    rs_bs_kernel<K, M, false, false><<<grid, kBsThreads, 4096, st>>>(p);
+  }
   return cudaGetLastError();
 }
 
