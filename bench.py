@@ -38,6 +38,24 @@ def shard_size(blob, k, min_shard=2048):
     return max((blob + k - 1) // k, min_shard)   # blobstore/common/ec/buf.go:77-81
 
 
+def measured_traffic(kernel: str, stripes: int):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the ncu --set full
+    capture summarised under profiles/ (taken at 1024 stripes; scaled linearly to this batch)."""
+    name = {"rs_bs_kernel<crc>": "r01_prof_r1_bs_crc.txt", "rs_bs_kernel": "r01_prof_r1_bs_nocrc.txt",
+            "rs_tabk_kernel": "r01_prof_tabk_rec.txt"}.get(kernel)
+    try:
+        txt = open(os.path.join(ROOT, "profiles", name)).read()
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            for line in txt.splitlines():
+                if line.startswith(key + " "):
+                    val, unit = line.split()[1], line.split()[2]
+                    tot += float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return int(tot * stripes / 1024) if tot else None
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -322,7 +340,7 @@ def main():
     # ---- end to end through the host entry point (pinned host buffers) ----
     e2e = None
     if not args.no_e2e and args.workload == "encode":
-        ns_e = min(ns, 256)
+        ns_e = min(ns, 512)
         host = torch.empty((ns_e, n * S), dtype=torch.uint8).pin_memory()
         host.copy_(torch.randint(0, 256, host.shape, dtype=torch.uint8))
         hnp = host.numpy()
@@ -352,7 +370,7 @@ def main():
         line["gpu_launches"] = int(launches)
         line["kernel"] = cb.last_kernel()
         line["roofline"] = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                            "frac": round(achieved / peak, 4), "traffic": measured_traffic(cb.last_kernel(), ns), "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": alg,
                             "note": "per-GPU figure; device time of one step (coding kernel + CRC finalize) by CUDA events"}
         line["e2e"] = e2e

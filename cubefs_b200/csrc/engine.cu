@@ -1210,8 +1210,9 @@ int encode_contig_device(cubeec* h, DevCtx* c, uint8_t* base, size_t S, size_t f
   const size_t P = round_up(S, kAlign);
   const size_t dstripe = P * n;
   std::lock_guard<std::mutex> bulk(c->bulk_mu);
-  // chunk: up to ~256 MiB of device staging per lane
-  size_t chunk = std::max<size_t>(1, (256u << 20) / dstripe);
+  // chunk: ~96 MiB of device staging per lane -- small enough that the fill / drain of the
+  // H2D -> kernel -> D2H pipeline is a small part of a batch, large enough to amortise launches
+  size_t chunk = std::max<size_t>(1, (96u << 20) / dstripe);
   chunk = std::min(chunk, count);
   const int n_lanes = 3;
   // CRC scratch bound for any chunk of <= `chunk` stripes: nb * n_seg(nb) <= 8*SMs + nb
