@@ -35,11 +35,6 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-// pull a 32-byte column into L2 ahead of time (no register cost): the register-level look-ahead of
-// two shards only has to cover L2 latency afterwards
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -425,11 +420,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bsrec_kernel(const BsRecPara
     const size_t seg_start = (size_t)seg * seg_bytes;
 
     // one 32-byte column group; FULL = whole tile inside the shard (no predicates / tail masks)
-    auto group = [&](auto full_tag, const size_t col, const size_t next_col) {
+    auto group = [&](auto full_tag, const size_t col) {
       constexpr bool FULL = decltype(full_tag)::value;
       const bool live = FULL || col < p.shard_len;
       const int tail = (!FULL && live && col + 32 > p.shard_len) ? (int)(p.shard_len - col) : 0;
-      (void)next_col;
       uint32_t acc[8 * M];
 #pragma unroll
       for (int i = 0; i < 8 * M; i++) acc[i] = 0;
@@ -547,12 +541,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bsrec_kernel(const BsRecPara
       const size_t col0 = tile_start + (size_t)tid * kBsPiece;
       if (tile_start + kBsTile <= p.shard_len) {
 #pragma unroll 1
-        for (int g = 0; g < kBsGroups; g++)
-          group(std::true_type{}, col0 + (size_t)g * 32, g + 1 < kBsGroups ? col0 + (size_t)(g + 1) * 32 : (t + 1 < T ? col0 + kBsTile : (size_t)-1));
+        for (int g = 0; g < kBsGroups; g++) group(std::true_type{}, col0 + (size_t)g * 32);
       } else {
 #pragma unroll 1
-        for (int g = 0; g < kBsGroups; g++)
-          group(std::false_type{}, col0 + (size_t)g * 32, g + 1 < kBsGroups ? col0 + (size_t)(g + 1) * 32 : (t + 1 < T ? col0 + kBsTile : (size_t)-1));
+        for (int g = 0; g < kBsGroups; g++) group(std::false_type{}, col0 + (size_t)g * 32);
       }
     }
   }

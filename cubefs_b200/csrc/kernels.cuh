@@ -115,7 +115,6 @@ constexpr int kBsTile = kBsThreads * kBsPiece;                // bytes of every 
 constexpr int kBsFoldCopies = 4;
 constexpr int kBsPackedMaxStripes = 72;                       // stripes a packed tile can touch (pieces/shard >= 8)
 constexpr size_t kBsSliceImageBytes = 2 * 65536;
-constexpr size_t kBsMiscBytes = 4 * 256 * kBsFoldCopies * 4 + kBsThreads * 4 + 64;
 constexpr size_t kBsSmemBytes = 65536 + kBsSliceImageBytes + 1024;
 
 struct BsParams {

@@ -461,3 +461,37 @@ def test_small_shards_packed_mode(cb, oracle, km):
         ora.encode_batch_simd(want, S, S, n * S, ns)
         assert (out[:, :, :S] == want).all(), (km, S)
         assert all(crc[s, i] == zlib.crc32(want[s, i].tobytes()) for s in range(ns) for i in range(n)), (km, S)
+
+
+def test_concurrent_callers(cb, oracle):
+    """ec.Encoder methods are called from many goroutines at once (encoder.go:115, Concurrency up to 1000):
+    the C-ABI must be thread-safe.  16 threads x mixed encode / verify / reconstruct / crc32 on one handle."""
+    import threading
+    k, m = 12, 4
+    eng = cb.RSEngine(k, m)
+    ora = oracle.RS(k, m)
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for it in range(6):
+                S = int(rng.integers(1, 200000))
+                sh = [rng.integers(0, 256, S, dtype=np.uint8) for _ in range(k)] + [np.zeros(S, np.uint8) for _ in range(m)]
+                want = [x.copy() for x in sh]
+                ora.encode(want)
+                crc = eng.encode(sh, crc=True)
+                assert all((a == b).all() for a, b in zip(sh, want))
+                assert [int(c) for c in crc] == [zlib.crc32(w.tobytes()) for w in want]
+                assert eng.verify(sh)
+                miss = rng.choice(k + m, size=int(rng.integers(1, m + 1)), replace=False)
+                out = eng.reconstruct([None if i in miss else want[i] for i in range(k + m)])
+                assert all((a == b).all() for a, b in zip(out, want))
+                assert cb.crc32(want[0]) == zlib.crc32(want[0].tobytes())
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(16)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors[:3]
