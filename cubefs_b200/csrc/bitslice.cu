@@ -46,6 +46,19 @@ __device__ __forceinline__ uint32_t lds32_off(uint32_t addr) {
   asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
   return v;
 }
+// base + mult * byte B of w in ONE instruction on the FMA pipe: IDP.2A (dp2a) multiplies the two 16-bit
+// halves of `m` with two bytes of `w` (.lo: bytes 0,1; .hi: bytes 2,3) and adds `base`.  m = MULT selects
+// the even byte, m = MULT << 16 the odd one.  This replaces PRMT (ALU pipe) for lookup addresses:
+// the kernels are bound by the ALU pipe (LOP3/SHF/PRMT) while the FMA pipe idles.
+template <int B>
+__device__ __forceinline__ uint32_t byte_madd(uint32_t w, uint32_t m_even, uint32_t m_odd, uint32_t base) {
+  uint32_t d;
+  if (B == 0) asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(m_even), "r"(w), "r"(base));
+  if (B == 1) asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(m_odd), "r"(w), "r"(base));
+  if (B == 2) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(m_even), "r"(w), "r"(base));
+  if (B == 3) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(m_odd), "r"(w), "r"(base));
+  return d;
+}
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t d;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
@@ -171,11 +184,11 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
 
   // one slicing-by-4 step: register after absorbing the 4 bytes of y (= state ^ data word)
   auto slice4 = [&](uint32_t y) -> uint32_t {
-    // lookup address = (table hi) | byte << 8 | lane*4: one PRMT per byte
-    const uint32_t a0 = prmt(y, lane_base, 0x7604u);
-    const uint32_t a1 = prmt(y, lane_base, 0x7614u);
-    const uint32_t a2 = prmt(y, lane_base, 0x7624u);
-    const uint32_t a3 = prmt(y, lane_base, 0x7634u);
+    // lookup address = table base + lane*4 + byte * 256: one IDP.2A per byte (FMA pipe)
+    const uint32_t a0 = byte_madd<0>(y, 256u, 256u << 16, lane_base);
+    const uint32_t a1 = byte_madd<1>(y, 256u, 256u << 16, lane_base);
+    const uint32_t a2 = byte_madd<2>(y, 256u, 256u << 16, lane_base);
+    const uint32_t a3 = byte_madd<3>(y, 256u, 256u << 16, lane_base);
     // byte0 -> table 3, byte1 -> table 2, byte2 -> table 1, byte3 -> table 0
     const uint32_t t3 = lds32_off<65536 + 128>(a0);
     const uint32_t t2 = lds32_off<65536>(a1);
@@ -186,9 +199,9 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
   auto fold = [&](uint32_t u) -> uint32_t {
     const uint32_t* f = fold_s;
     (void)f;
-    const uint32_t b0 = (u & 0xffu), b1 = (u >> 8) & 0xffu, b2 = (u >> 16) & 0xffu, b3 = u >> 24;
-    return lds32(fold_lane + (0 * 256 + b0) * (kBsFoldCopies * 4)) ^ lds32(fold_lane + (1 * 256 + b1) * (kBsFoldCopies * 4)) ^
-           lds32(fold_lane + (2 * 256 + b2) * (kBsFoldCopies * 4)) ^ lds32(fold_lane + (3 * 256 + b3) * (kBsFoldCopies * 4));
+    constexpr uint32_t ST = kBsFoldCopies * 4;   // bytes per table entry group
+    return lds32(byte_madd<0>(u, ST, ST << 16, fold_lane + 0 * 256 * ST)) ^ lds32(byte_madd<1>(u, ST, ST << 16, fold_lane + 1 * 256 * ST)) ^
+           lds32(byte_madd<2>(u, ST, ST << 16, fold_lane + 2 * 256 * ST)) ^ lds32(byte_madd<3>(u, ST, ST << 16, fold_lane + 3 * 256 * ST));
   };
 
   uint32_t crc_u[K + M];
@@ -495,15 +508,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bsrec_kernel(const BsRecPara
 #pragma unroll
             for (int q = 0; q < 4; q++) {
               const uint32_t w = acc[r * 8 + hh * 4 + q];
-              uint32_t a0, a1, a2, a3;
-              asm("prmt.b32 %0, %1, 0, 0x4440;" : "=r"(a0) : "r"(w));
-              asm("prmt.b32 %0, %1, 0, 0x4441;" : "=r"(a1) : "r"(w));
-              asm("prmt.b32 %0, %1, 0, 0x4442;" : "=r"(a2) : "r"(w));
-              asm("prmt.b32 %0, %1, 0, 0x4443;" : "=r"(a3) : "r"(w));
-              packed[q * 4 + 0] ^= lds32(a0 * 256u + tb);
-              packed[q * 4 + 1] ^= lds32(a1 * 256u + tb);
-              packed[q * 4 + 2] ^= lds32(a2 * 256u + tb);
-              packed[q * 4 + 3] ^= lds32(a3 * 256u + tb);
+              packed[q * 4 + 0] ^= lds32(byte_madd<0>(w, 256u, 256u << 16, tb));
+              packed[q * 4 + 1] ^= lds32(byte_madd<1>(w, 256u, 256u << 16, tb));
+              packed[q * 4 + 2] ^= lds32(byte_madd<2>(w, 256u, 256u << 16, tb));
+              packed[q * 4 + 3] ^= lds32(byte_madd<3>(w, 256u, 256u << 16, tb));
             }
             si++;
           }

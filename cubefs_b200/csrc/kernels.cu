@@ -61,17 +61,15 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-// byte B of w, zero-extended (one PRMT)
+// table lookup address = base + 256 * (byte B of w) in ONE instruction on the FMA pipe: IDP.2A (dp2a)
+// multiplies the 16-bit halves of its first operand with two bytes of w (.lo: bytes 0,1; .hi: 2,3).
 template <int B>
-__device__ __forceinline__ uint32_t byte_of(uint32_t w) {
+__device__ __forceinline__ uint32_t row_addr_b(uint32_t w, uint32_t base) {
   uint32_t d;
-  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(w), "n"(0x4440 + B));
-  return d;
-}
-// table lookup address: v * 256 + base  (multiply-add on the FMA pipe)
-__device__ __forceinline__ uint32_t row_addr(uint32_t v, uint32_t base) {
-  uint32_t d;
-  asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(d) : "r"(v), "r"(base));
+  if (B == 0) asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(256u), "r"(w), "r"(base));
+  if (B == 1) asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(256u << 16), "r"(w), "r"(base));
+  if (B == 2) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(256u), "r"(w), "r"(base));
+  if (B == 3) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(256u << 16), "r"(w), "r"(base));
   return d;
 }
 
@@ -275,10 +273,10 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tab_kernel(const TabParams 
             const uint32_t w[4] = {dd.x, dd.y, dd.z, dd.w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-              acc[q * 4 + 0] ^= lds_u32(row_addr(byte_of<0>(w[q]), tb));
-              acc[q * 4 + 1] ^= lds_u32(row_addr(byte_of<1>(w[q]), tb));
-              acc[q * 4 + 2] ^= lds_u32(row_addr(byte_of<2>(w[q]), tb));
-              acc[q * 4 + 3] ^= lds_u32(row_addr(byte_of<3>(w[q]), tb));
+              acc[q * 4 + 0] ^= lds_u32(row_addr_b<0>(w[q], tb));
+              acc[q * 4 + 1] ^= lds_u32(row_addr_b<1>(w[q], tb));
+              acc[q * 4 + 2] ^= lds_u32(row_addr_b<2>(w[q], tb));
+              acc[q * 4 + 3] ^= lds_u32(row_addr_b<3>(w[q], tb));
             }
             if (crc_in) {
               uint32_t* st = crc_st + (size_t)cc * NT + tid;
@@ -443,15 +441,15 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tabk_kernel(const TabParams
 #pragma unroll
             for (int q = 0; q < 4; q++) {
               if (two) {
-                acc[q * 4 + 0] ^= lds_u32(row_addr(byte_of<0>(wa[q]), ta)) ^ lds_u32(row_addr(byte_of<0>(wb[q]), tb));
-                acc[q * 4 + 1] ^= lds_u32(row_addr(byte_of<1>(wa[q]), ta)) ^ lds_u32(row_addr(byte_of<1>(wb[q]), tb));
-                acc[q * 4 + 2] ^= lds_u32(row_addr(byte_of<2>(wa[q]), ta)) ^ lds_u32(row_addr(byte_of<2>(wb[q]), tb));
-                acc[q * 4 + 3] ^= lds_u32(row_addr(byte_of<3>(wa[q]), ta)) ^ lds_u32(row_addr(byte_of<3>(wb[q]), tb));
+                acc[q * 4 + 0] ^= lds_u32(row_addr_b<0>(wa[q], ta)) ^ lds_u32(row_addr_b<0>(wb[q], tb));
+                acc[q * 4 + 1] ^= lds_u32(row_addr_b<1>(wa[q], ta)) ^ lds_u32(row_addr_b<1>(wb[q], tb));
+                acc[q * 4 + 2] ^= lds_u32(row_addr_b<2>(wa[q], ta)) ^ lds_u32(row_addr_b<2>(wb[q], tb));
+                acc[q * 4 + 3] ^= lds_u32(row_addr_b<3>(wa[q], ta)) ^ lds_u32(row_addr_b<3>(wb[q], tb));
               } else {
-                acc[q * 4 + 0] ^= lds_u32(row_addr(byte_of<0>(wa[q]), ta));
-                acc[q * 4 + 1] ^= lds_u32(row_addr(byte_of<1>(wa[q]), ta));
-                acc[q * 4 + 2] ^= lds_u32(row_addr(byte_of<2>(wa[q]), ta));
-                acc[q * 4 + 3] ^= lds_u32(row_addr(byte_of<3>(wa[q]), ta));
+                acc[q * 4 + 0] ^= lds_u32(row_addr_b<0>(wa[q], ta));
+                acc[q * 4 + 1] ^= lds_u32(row_addr_b<1>(wa[q], ta));
+                acc[q * 4 + 2] ^= lds_u32(row_addr_b<2>(wa[q], ta));
+                acc[q * 4 + 3] ^= lds_u32(row_addr_b<3>(wa[q], ta));
               }
             }
           }

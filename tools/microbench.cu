@@ -12,7 +12,7 @@
 constexpr int ITERS = 2048;
 constexpr int CH = 8;   // independent chains per thread
 
-enum Op { LOP3, IMAD, IMADHI, SHF, PRMT, IADD3, MIX_LOP_IMAD, MIX_LOP_IMADHI, MIX_LOP_SHF, MIX_LOP_PRMT, POPC, IMAD_SHL };
+enum Op { LOP3, IMAD, IMADHI, SHF, PRMT, IADD3, MIX_LOP_IMAD, MIX_LOP_IMADHI, MIX_LOP_SHF, MIX_LOP_PRMT, POPC, IMAD_SHL, DP2A, DP4A, MIX_LOP_DP2A, MIX_LOP2_DP2A };
 
 template <int OP>
 __global__ void alu_kernel(uint32_t* out, long long* cycles, uint32_t seed) {
@@ -34,6 +34,16 @@ __global__ void alu_kernel(uint32_t* out, long long* cycles, uint32_t seed) {
       else if (OP == IADD3) { asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i])); }
       else if (OP == POPC) { asm volatile("popc.b32 %0, %0;" : "+r"(a[i])); }
       else if (OP == IMAD_SHL) { asm volatile("mul.lo.u32 %0, %0, 16;" : "+r"(a[i])); }
+      else if (OP == DP2A) { asm volatile("dp2a.lo.u32.u32 %0, %1, %0, %2;" : "+r"(a[i]) : "r"(k2), "r"(b[i])); }
+      else if (OP == DP4A) { asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(k2), "r"(b[i])); }
+      else if (OP == MIX_LOP_DP2A) {
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(k1));
+        asm volatile("dp2a.lo.u32.u32 %0, %1, %0, %2;" : "+r"(b[i]) : "r"(k2), "r"(k1));
+      } else if (OP == MIX_LOP2_DP2A) {
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(k1));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(k2));
+        asm volatile("dp2a.hi.u32.u32 %0, %1, %0, %2;" : "+r"(b[i]) : "r"(k2), "r"(k1));
+      }
       else if (OP == MIX_LOP_IMAD) {
         asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(k1));
         asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b[i]) : "r"(k1), "r"(k2));
@@ -160,6 +170,10 @@ int main() {
   run_alu("PRMT", alu_kernel<PRMT>, 1, sms);
   run_alu("IADD", alu_kernel<IADD3>, 1, sms);
   run_alu("POPC", alu_kernel<POPC>, 1, sms);
+  run_alu("DP2A", alu_kernel<DP2A>, 1, sms);
+  run_alu("DP4A", alu_kernel<DP4A>, 1, sms);
+  run_alu("LOP3+DP2A", alu_kernel<MIX_LOP_DP2A>, 2, sms);
+  run_alu("2xLOP3+DP2A", alu_kernel<MIX_LOP2_DP2A>, 3, sms);
   run_alu("LOP3+IMAD", alu_kernel<MIX_LOP_IMAD>, 2, sms);
   run_alu("LOP3+IMAD.HI", alu_kernel<MIX_LOP_IMADHI>, 2, sms);
   run_alu("LOP3+SHF", alu_kernel<MIX_LOP_SHF>, 2, sms);
