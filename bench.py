@@ -41,7 +41,7 @@ def shard_size(blob, k, min_shard=2048):
 def measured_traffic(kernel: str, stripes: int):
     """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the ncu --set full
     capture summarised under profiles/ (taken at 1024 stripes; scaled linearly to this batch)."""
-    name = {"rs_bs_kernel<crc>": "r01_prof_r1_bs_crc.txt", "rs_bs_kernel": "r01_prof_r1_bs_nocrc.txt",
+    name = {"rs_bsw_kernel": "r01_prof_bsw.txt", "rs_bs_kernel<crc>": "r01_prof_r1_bs_crc.txt", "rs_bs_kernel": "r01_prof_r1_bs_nocrc.txt",
             "rs_tabk_kernel": "r01_prof_tabk_rec.txt"}.get(kernel)
     try:
         txt = open(os.path.join(ROOT, "profiles", name)).read()
@@ -245,7 +245,8 @@ def main():
     ap.add_argument("--cpu-stripes", type=int, default=256, help="stripes in the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "table"], help="A/B aid: force the generic table kernel")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "table", "ws"],
+                    help="A/B aid: table = generic table kernel, ws = warp-specialised fused encode+CRC kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -271,6 +272,8 @@ def main():
     cb.init([local_rank])
     if args.kernel == "table":
         cb.force_kernel(1)
+    if args.kernel == "ws":
+        cb.force_kernel(5)
 
     # coding matrix: built on rank 0, NCCL-broadcast to the other ranks (the only shared state)
     if rank == 0:

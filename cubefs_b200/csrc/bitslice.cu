@@ -18,115 +18,18 @@
 
 #include "bs_net_gen.cuh"
 #include "kernels.cuh"
+#include "bs_device.cuh"
 
 namespace cbe {
 
-namespace {
+using namespace bsdev;
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
-  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
-  asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-template <int IMM>
-__device__ __forceinline__ uint32_t lds32_off(uint32_t addr) {
-  uint32_t v;
-  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
-  return v;
-}
-// base + mult * byte B of w in ONE instruction on the FMA pipe: IDP.2A (dp2a) multiplies the two 16-bit
-// halves of `m` with two bytes of `w` (.lo: bytes 0,1; .hi: bytes 2,3) and adds `base`.  m = MULT selects
-// the even byte, m = MULT << 16 the odd one.  This replaces PRMT (ALU pipe) for lookup addresses:
-// the kernels are bound by the ALU pipe (LOP3/SHF/PRMT) while the FMA pipe idles.
-template <int B>
-__device__ __forceinline__ uint32_t byte_madd(uint32_t w, uint32_t m_even, uint32_t m_odd, uint32_t base) {
-  uint32_t d;
-  if (B == 0) asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(m_even), "r"(w), "r"(base));
-  if (B == 1) asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(m_odd), "r"(w), "r"(base));
-  if (B == 2) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(m_even), "r"(w), "r"(base));
-  if (B == 3) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(m_odd), "r"(w), "r"(base));
-  return d;
-}
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-  return d;
-}
-
-// 8x8 bit transpose across 8 words, independently in each of the 4 byte lanes (an involution):
-// afterwards word j holds bit j of all 32 bytes.  12 delta swaps = 24 LOP3 + 12 right shifts
-// (ALU pipe) + 12 left shifts written as multiplies (FMA pipe).
-// d = (a & MASK) | (b & ~MASK) in ONE LOP3 (lut 0xE4 with the mask as the immediate operand)
-template <uint32_t MASK>
-__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "n"(MASK));
-  return d;
-}
-// (Measured: moving the right shifts or the byte-0 address to IMAD.HI on the FMA pipe does not
-// pay -- IMAD.HI issues at a quarter of the IMAD rate and lengthens the serial CRC chain.)
-template <int S, uint32_t MASK>
-__device__ __forceinline__ void delta_swap(uint32_t& a, uint32_t& b) {
-  const uint32_t na = bitsel<MASK>(a, b * (1u << S));
-  const uint32_t nb = bitsel<MASK>(a >> S, b);
-  a = na;
-  b = nb;
-}
-__device__ __forceinline__ void bit_transpose8(uint32_t (&w)[8]) {
-  delta_swap<4, 0x0f0f0f0fu>(w[0], w[4]);
-  delta_swap<4, 0x0f0f0f0fu>(w[1], w[5]);
-  delta_swap<4, 0x0f0f0f0fu>(w[2], w[6]);
-  delta_swap<4, 0x0f0f0f0fu>(w[3], w[7]);
-  delta_swap<2, 0x33333333u>(w[0], w[2]);
-  delta_swap<2, 0x33333333u>(w[1], w[3]);
-  delta_swap<2, 0x33333333u>(w[4], w[6]);
-  delta_swap<2, 0x33333333u>(w[5], w[7]);
-  delta_swap<1, 0x55555555u>(w[0], w[1]);
-  delta_swap<1, 0x55555555u>(w[2], w[3]);
-  delta_swap<1, 0x55555555u>(w[4], w[5]);
-  delta_swap<1, 0x55555555u>(w[6], w[7]);
-}
-
-__device__ __forceinline__ uint32_t gf32_mul_dev(uint32_t a, uint32_t b, uint32_t poly) {
-  uint32_t r = 0;
-#pragma unroll 8
-  for (int i = 0; i < 32; i++) {
-    r ^= a & (uint32_t)((int32_t)b >> 31);
-    b <<= 1;
-    a = (a >> 1) ^ (poly & (0u - (a & 1u)));
-  }
-  return r;
-}
-
-// compile-time dispatch on the shard index
-template <class Net, int C, int K>
-struct ApplyAt {
-  static __device__ __forceinline__ void run(int c, const uint32_t (&w)[8], uint32_t (&acc)[8 * Net::M]) {
-    if (c == C) Net::template apply<C>(w, acc);
-    else ApplyAt<Net, C + 1, K>::run(c, w, acc);
-  }
-};
-template <class Net, int K>
-struct ApplyAt<Net, K, K> {
-  static __device__ __forceinline__ void run(int, const uint32_t (&)[8], uint32_t (&)[8 * Net::M]) {}
-};
-
-}  // namespace
-
-template <int K, int M, bool CRC, bool PACKED>
+// VERIFY (reedSolomon.Verify / checkSomeShards, RS/reedsolomon.go:770-784,1287-1301): the computed
+// parity is compared with the stored parity instead of being written; any difference raises the
+// stripe's flag in p.mismatch.  The reference allocates m scratch shards and runs bytes.Equal.
+template <int K, int M, bool CRC, bool PACKED, bool VERIFY = false>
 __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) {
+  static_assert(!(CRC && VERIFY), "verify does not checksum");
   using Net = BsNet<K, M>;
   constexpr int NT = kBsThreads, NW = NT / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -207,6 +110,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
   uint32_t crc_u[K + M];
 #pragma unroll
   for (int i = 0; i < K + M; i++) crc_u[i] = 0;
+  uint32_t vdiff = 0;   // VERIFY: OR of (computed ^ stored) parity words of this thread
 
   // (an explicit prefetch.global.L2 of the next column group was measured: 30 % slower -- not used)
   // one 32-byte group of every shard.  FULL = the whole tile lies inside [0, shard_len): no
@@ -264,7 +168,16 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
 #pragma unroll
       for (int i = 0; i < 8; i++) o[i] = acc[r * 8 + i];
       bit_transpose8(o);
-      if (live) stg256(sbase + (size_t)(K + r) * p.shard_pitch + col, o);
+      if (VERIFY) {
+        if (live) {
+          uint32_t e[8];
+          ldg256(sbase + (size_t)(K + r) * p.shard_pitch + col, e);
+#pragma unroll
+          for (int i = 0; i < 8; i++) vdiff |= o[i] ^ (FULL ? e[i] : (e[i] & msk[i]));
+        }
+      } else if (live) {
+        stg256(sbase + (size_t)(K + r) * p.shard_pitch + col, o);
+      }
       if (CRC) {
         uint32_t u = crc_u[K + r];
 #pragma unroll
@@ -292,6 +205,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
         uint8_t* sb = p.base + (size_t)stripe * p.stripe_pitch;
 #pragma unroll 1
         for (int g = 0; g < kBsGroups; g++) group(std::false_type{}, sb, (size_t)pos * kBsPiece + (size_t)g * 32);
+        if (VERIFY && vdiff) p.mismatch[stripe] = 1;
+        vdiff = 0;
       }
       if (CRC && p.crc_part) {
         const uint32_t stripe0 = (uint32_t)(((uint64_t)tile * NT) / PPS);
@@ -347,6 +262,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
       }
     }
 
+    if (VERIFY) {
+      if (vdiff) p.mismatch[s] = 1;   // benign race: every writer stores the same value
+      vdiff = 0;
+    }
     if (CRC && p.crc_part) {
       const uint32_t kt = kth_s[tid];
 #pragma unroll
@@ -577,7 +496,7 @@ static bool rows_match(const uint8_t* rows) {
 }
 
 template <int K, int M>
-static cudaError_t launch_cfg(const BsParams& p, bool crc, int grid, cudaStream_t st) {
+static cudaError_t launch_cfg(const BsParams& p, bool crc, bool verify, int grid, cudaStream_t st) {
   static bool configured = false;   // per process; attribute is per device function, set for every device lazily
   cudaError_t e;
   (void)configured;
@@ -586,6 +505,9 @@ static cudaError_t launch_cfg(const BsParams& p, bool crc, int grid, cudaStream_
     auto kern = packed ? rs_bs_kernel<K, M, true, true> : rs_bs_kernel<K, M, true, false>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsSmemBytes)) != cudaSuccess) return e;
     kern<<<grid, kBsThreads, kBsSmemBytes, st>>>(p);
+  } else if (verify) {
+    if (packed) rs_bs_kernel<K, M, false, true, true><<<grid, kBsThreads, 4096, st>>>(p);
+    else rs_bs_kernel<K, M, false, false, true><<<grid, kBsThreads, 4096, st>>>(p);
   } else if (packed) {
     rs_bs_kernel<K, M, false, true><<<grid, kBsThreads, 4096, st>>>(p);
   } else {
@@ -612,9 +534,10 @@ cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStre
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_bs(int k, int m, const BsParams& p, bool crc, int grid, cudaStream_t st) {
+cudaError_t launch_bs(int k, int m, const BsParams& p, bool crc, bool verify, int grid, cudaStream_t st) {
+  if (crc && verify) return cudaErrorInvalidValue;
 #define X(KK, MM) \
-  if (k == KK && m == MM) return launch_cfg<KK, MM>(p, crc, grid, st);
+  if (k == KK && m == MM) return launch_cfg<KK, MM>(p, crc, verify, grid, st);
   CUBEEC_BS_CONFIGS(X)
 #undef X
   return cudaErrorInvalidValue;

@@ -91,6 +91,9 @@ struct DevCtx {
   uint32_t* d_bs_slice[2] = {nullptr, nullptr};
   uint32_t* d_bs_fold[2] = {nullptr, nullptr};
   uint32_t* d_bs_kthread[2] = {nullptr, nullptr};
+  // the same two for the tile of the warp-specialised kernel (bitslice_ws.cu)
+  uint32_t* d_bsw_fold[2] = {nullptr, nullptr};
+  uint32_t* d_bsw_kthread[2] = {nullptr, nullptr};
   std::mutex mu;
   std::condition_variable cv;
   std::vector<Lane*> free_lanes;
@@ -149,6 +152,13 @@ int setup_device(DevCtx& c) {
     CU(cudaMemcpy(c.d_bs_fold[pi], fold, sizeof(fold), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c.d_bs_kthread[pi], kth.size() * 4));
     CU(cudaMemcpy(c.d_bs_kthread[pi], kth.data(), kth.size() * 4, cudaMemcpyHostToDevice));
+    crc_const_mul_tables(P, P.shift_bytes_const((int64_t)kBswTile - kBsPiece), fold);
+    kth.assign(kBswE, 0);
+    for (int t = 0; t < kBswE; t++) kth[t] = P.shift_bytes_const((int64_t)kBswTile - (int64_t)kBsPiece * (t + 1));
+    CU(cudaMalloc(&c.d_bsw_fold[pi], sizeof(fold)));
+    CU(cudaMemcpy(c.d_bsw_fold[pi], fold, sizeof(fold), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c.d_bsw_kthread[pi], kth.size() * 4));
+    CU(cudaMemcpy(c.d_bsw_kthread[pi], kth.data(), kth.size() * 4, cudaMemcpyHostToDevice));
   }
   return CUBEEC_OK;
 }
@@ -407,7 +417,7 @@ Geometry pick_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes, bool
   uint64_t want_items = (uint64_t)c.sm_count * (per_stripe_patterns ? 2 : 8);
   if (n_stripes >= (uint64_t)c.sm_count * 4) want_items = n_stripes;
   uint64_t n_seg = (want_items + n_stripes - 1) / std::max<size_t>(n_stripes, 1);
-  const uint64_t max_seg = std::max<uint64_t>(1, tiles_total / (tile >= 32768 ? 1 : 4));
+  const uint64_t max_seg = std::max<uint64_t>(1, tiles_total / (tile >= 16384 ? 1 : 4));
   n_seg = std::max<uint64_t>(1, std::min(n_seg, max_seg));
   uint64_t tps = (tiles_total + n_seg - 1) / n_seg;
   n_seg = (tiles_total + tps - 1) / tps;
@@ -533,7 +543,8 @@ size_t crc_part_bytes(const DevCtx& c, size_t shard_len, size_t n_stripes, int n
   // upper bound over both kernels' geometries
   const Geometry g1 = pick_geometry(c, shard_len, n_stripes, false);
   const Geometry g2 = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
-  return n_stripes * (size_t)n_slots * std::max<uint32_t>(std::max(g1.n_seg, g2.n_seg), 2u) * sizeof(uint32_t);
+  const Geometry g3 = pick_geometry(c, shard_len, n_stripes, false, kBswTile);
+  return n_stripes * (size_t)n_slots * std::max<uint32_t>(std::max(std::max(g1.n_seg, g2.n_seg), g3.n_seg), 2u) * sizeof(uint32_t);
 }
 
 // The bit-sliced kernel needs 32-byte columns: base and pitches 32-aligned, room for whole groups.
@@ -552,12 +563,16 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
   const int n = h->k + h->m;
   const size_t ci = ctx_index(&c);
   const bool want_crc = mode == 0 && d_crc_out;
-  if (mode == 0 && h->bs_ok && g_force_kernel.load() != 1 && bs_layout_ok(d_base, shard_len, shard_pitch, stripe_pitch)) {
+  if (h->bs_ok && g_force_kernel.load() != 1 && bs_layout_ok(d_base, shard_len, shard_pitch, stripe_pitch)) {
     // hot path: bit-sliced XOR-network kernel (bitslice.cu)
     Geometry gm = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
     // shards shorter than a tile: packed mode (pieces of many stripes share a tile)
     const uint32_t pps = (uint32_t)((shard_len + kBsPiece - 1) / kBsPiece);
     const bool packed = pps < (uint32_t)kBsThreads && pps >= 8;
+    // opt-in A/B aid: the warp-specialised fused kernel (bitslice_ws.cu; measured within +-3 % of
+    // rs_bs_kernel<crc>, see DESIGN.md "issue ceiling")
+    const bool ws = want_crc && !packed && g_force_kernel.load() == 5 && bsw_supported(h->k, h->m);
+    if (ws) gm = pick_geometry(c, shard_len, n_stripes, false, kBswTile);
     if (packed) {
       const uint64_t tiles = ((uint64_t)n_stripes * pps + kBsThreads - 1) / kBsThreads;
       gm.n_seg = 2;               // a shard's pieces fall into at most two tiles
@@ -582,16 +597,18 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
     bp.tiles_last = gm.tiles_last;
     bp.n_slots = (uint32_t)n;
     bp.crc_part = want_crc ? d_part : nullptr;
+    bp.mismatch = mode == 1 ? d_mismatch : nullptr;
     const int pi = crc_poly ? 1 : 0;
     bp.slice_image = c.d_bs_slice[pi];
-    bp.fold_tables = c.d_bs_fold[pi];
-    bp.kthread = c.d_bs_kthread[pi];
+    bp.fold_tables = ws ? c.d_bsw_fold[pi] : c.d_bs_fold[pi];
+    bp.kthread = ws ? c.d_bsw_kthread[pi] : c.d_bs_kthread[pi];
     bp.poly = g.poly[pi].poly;
     bp.k65536 = 65536u;
     bp.packed_pps = gm.packed_pps;
-    CU(launch_bs(h->k, h->m, bp, want_crc, gm.grid, stream));
+    if (ws) CU(launch_bsw(h->k, h->m, bp, gm.grid, stream));
+    else CU(launch_bs(h->k, h->m, bp, want_crc, mode == 1, gm.grid, stream));
     g_launches++;
-    t_last_kernel = want_crc ? "rs_bs_kernel<crc>" : "rs_bs_kernel";
+    t_last_kernel = ws ? "rs_bsw_kernel" : want_crc ? "rs_bs_kernel<crc>" : mode == 1 ? "rs_bs_kernel<verify>" : "rs_bs_kernel";
     if (want_crc) {
       int rc = finalize_crc(c, stream, d_part, n_stripes, n, shard_len, gm, crc_poly, nullptr, d_crc_out);
       if (rc) return rc;

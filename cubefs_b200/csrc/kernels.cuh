@@ -116,6 +116,19 @@ constexpr int kBsFoldCopies = 4;
 constexpr int kBsPackedMaxStripes = 72;                       // stripes a packed tile can touch (pieces/shard >= 8)
 constexpr size_t kBsSliceImageBytes = 2 * 65536;
 constexpr size_t kBsSmemBytes = 65536 + kBsSliceImageBytes + 1024;
+// warp-specialised fused encode+CRC kernel (bitslice_ws.cu): kBswE coder threads (XOR network, parity
+// CRC) and kBswC checksum threads (data-shard CRC) per CTA; the coder threads define the tile.
+#ifndef CUBEEC_BSW_E
+#define CUBEEC_BSW_E 256
+#define CUBEEC_BSW_C 384
+#define CUBEEC_BSW_RE 176
+#define CUBEEC_BSW_RC 40
+#endif
+constexpr int kBswE = CUBEEC_BSW_E;
+constexpr int kBswC = CUBEEC_BSW_C;
+constexpr int kBswTile = kBswE * kBsPiece;
+// setmaxnreg budgets: kBswRegsE * kBswE + kBswRegsC * kBswC <= registers the launch allocates
+constexpr int kBswRegsE = CUBEEC_BSW_RE, kBswRegsC = CUBEEC_BSW_RC;
 
 struct BsParams {
   uint8_t* base;
@@ -124,6 +137,7 @@ struct BsParams {
   uint32_t n_seg, tiles_per_seg, tiles_last;
   uint32_t n_slots;
   uint32_t* crc_part;                 // [n_stripes][n_slots][n_seg] or nullptr
+  int32_t* mismatch;                  // verify variant: [n_stripes], set to 1 on any parity difference
   const uint32_t* slice_image;        // global: 128 KiB replicated slicing tables (kBsSliceImageBytes)
   const uint32_t* fold_tables;        // global: [4][256] register * x^(8*(tile - piece))
   const uint32_t* kthread;            // global: [kBsThreads] x^(8*(tile - piece*(tid+1)))
@@ -166,6 +180,8 @@ struct BsRecParams {
 
 bool bs_supported(int k, int m, const uint8_t* parity_rows);   // a specialised network exists for this matrix
 cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStream_t st);
-cudaError_t launch_bs(int k, int m, const BsParams& p, bool crc, int grid, cudaStream_t st);
+cudaError_t launch_bs(int k, int m, const BsParams& p, bool crc, bool verify, int grid, cudaStream_t st);
+bool bsw_supported(int k, int m);                              // bitslice_ws.cu has this configuration (and its register split is safe)
+cudaError_t launch_bsw(int k, int m, const BsParams& p, int grid, cudaStream_t st);
 
 }  // namespace cbe

@@ -8,7 +8,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "lib", "libcubeec.so")
+# CUBEEC_LIB: load an alternative build of the same ABI (kernel A/B experiments); default = the in-tree library
+_SO = os.environ.get("CUBEEC_LIB") or os.path.join(_HERE, "lib", "libcubeec.so")
 
 ERR = {
     0: "ok", 1: "ErrInvShardNum", 2: "ErrMaxShardNum", 3: "ErrTooFewShards", 4: "ErrShardNoData",

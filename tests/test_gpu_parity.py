@@ -311,6 +311,73 @@ def test_linearity_and_roundtrip_at_scale(cb):
     assert torch.equal(c[:, :, :S], good[:, :, :S])
 
 
+def test_bitsliced_verify_kernel(cb):
+    """rs_bs_kernel<verify> (reedSolomon.Verify, RS/reedsolomon.go:770-784): ok on encoded stripes;
+    one flipped bit in any parity OR data shard -- first byte, last byte, middle -- fails exactly that
+    stripe; bytes in the pitch padding beyond shard_len never matter.  Packed (small shard),
+    whole-stripe and segmented geometries."""
+    import torch
+    for (k, m, S, ns) in ((12, 4, 349526, 6), (6, 3, 4096 + 7, 40), (4, 2, 2048, 700), (20, 4, 70001, 3), (12, 4, 33, 5)):
+        n, P = k + m, (S + 127) // 128 * 128
+        rng = np.random.default_rng(S + k)
+        host = rng.integers(0, 256, (ns, n, P), dtype=np.uint8)
+        eng = cb.RSEngine(k, m)
+        dev = torch.from_numpy(host).cuda()
+        eng.dev_encode(dev.data_ptr(), S, P, n * P, ns)
+        dok = torch.zeros(ns, dtype=torch.int32, device="cuda")
+        eng.dev_verify(dev.data_ptr(), S, P, n * P, ns, dok.data_ptr())
+        assert cb.last_kernel() == "rs_bs_kernel<verify>"
+        torch.cuda.synchronize()
+        assert bool((dok == 1).all()), (k, m, S)
+        # garbage in the pitch padding of every shard: still ok
+        if P > S:
+            dev[:, :, S:] = 0xA5
+            eng.dev_verify(dev.data_ptr(), S, P, n * P, ns, dok.data_ptr())
+            torch.cuda.synchronize()
+            assert bool((dok == 1).all()), (k, m, S, "pad")
+        picks = [(0, 0, 0), (ns - 1, n - 1, S - 1), (ns // 2, k, S // 2), (ns // 3, k - 1, S - 1), (1 % ns, n - 1, 0)]
+        for (s, shard, pos) in picks:
+            dev[s, shard, pos] ^= 0x10
+            eng.dev_verify(dev.data_ptr(), S, P, n * P, ns, dok.data_ptr())
+            torch.cuda.synchronize()
+            want = torch.ones(ns, dtype=torch.int32)
+            want[s] = 0
+            assert torch.equal(dok.cpu(), want), (k, m, S, s, shard, pos)
+            dev[s, shard, pos] ^= 0x10
+
+
+def test_warp_specialised_fused_kernel(cb, oracle):
+    """Opt-in rs_bsw_kernel (coder warps + checksum warps, bitslice_ws.cu): same parity bytes and the
+    same CRCs (both polynomials) as the oracle, on whole-stripe and segmented geometries and on
+    shard lengths that end inside a 32-byte group / inside a tile."""
+    import torch
+    k, m = 12, 4
+    n = k + m
+    eng = cb.RSEngine(k, m)
+    ora = oracle.RS(k, m)
+    for (S, ns, poly) in ((349526, 3, 0), (24576 * 2, 2, 0), (24576 * 3 + 1, 2, 1), (33, 700, 0), (100001, 700, 1)):
+        P = (S + 127) // 128 * 128
+        rng = np.random.default_rng(S)
+        host = rng.integers(0, 256, (ns, n, P), dtype=np.uint8)
+        cb.force_kernel(5)
+        try:
+            dev = torch.from_numpy(host).cuda()
+            dcrc = torch.zeros(ns * n, dtype=torch.int32, device="cuda")
+            eng.dev_encode(dev.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr(), poly=poly)
+            assert cb.last_kernel() == "rs_bsw_kernel"
+            torch.cuda.synchronize()
+        finally:
+            cb.force_kernel(0)
+        out = dev.cpu().numpy()
+        crc = dcrc.cpu().numpy().view(np.uint32).reshape(ns, n)
+        for s in list(range(min(ns, 3))) + [ns - 1]:
+            sh = [host[s, i, :S].copy() for i in range(n)]
+            ora.encode(sh)
+            for i in range(n):
+                assert (out[s, i, :S] == sh[i]).all(), (S, s, i)
+                assert crc[s, i] == oracle.crc32(sh[i].tobytes(), poly), (S, s, i, poly)
+
+
 def test_kernel_selection_and_ab_equivalence(cb, oracle):
     """The bit-sliced kernel serves the specialised matrices on 32-byte-aligned layouts; the generic
     table kernel must produce the same bytes and CRCs (A/B through cubeec_debug_force_kernel)."""
