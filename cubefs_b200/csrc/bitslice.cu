@@ -201,12 +201,25 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
       const bool active = f < F;
       const uint32_t stripe = active ? (uint32_t)(f / PPS) : 0xFFFFFFFFu;
       const uint32_t pos = active ? (uint32_t)(f - (uint64_t)stripe * PPS) : 0u;
-      if (active) {
+      if constexpr (!CRC) {
+        // no Horner register to keep contiguous: in group g lane L takes 32-byte half-piece g*32+L of
+        // the warp's 32 pieces, so one 256-bit request of a warp is a contiguous 1 KiB (whole lines)
+#pragma unroll 1
+        for (int g = 0; g < kBsGroups; g++) {
+          const uint32_t hp = (uint32_t)g * 32u + (uint32_t)lane;
+          const uint64_t fh = (uint64_t)tile * NT + (uint64_t)warp * 32u + (hp >> 1);
+          if (fh < F) {
+            const uint32_t st = (uint32_t)(fh / PPS);
+            const uint32_t ps = (uint32_t)(fh - (uint64_t)st * PPS);
+            group(std::false_type{}, p.base + (size_t)st * p.stripe_pitch, (size_t)ps * kBsPiece + (size_t)(hp & 1u) * 32);
+            if (VERIFY && vdiff) p.mismatch[st] = 1;
+            vdiff = 0;
+          }
+        }
+      } else if (active) {
         uint8_t* sb = p.base + (size_t)stripe * p.stripe_pitch;
 #pragma unroll 1
         for (int g = 0; g < kBsGroups; g++) group(std::false_type{}, sb, (size_t)pos * kBsPiece + (size_t)g * 32);
-        if (VERIFY && vdiff) p.mismatch[stripe] = 1;
-        vdiff = 0;
       }
       if (CRC && p.crc_part) {
         const uint32_t stripe0 = (uint32_t)(((uint64_t)tile * NT) / PPS);
@@ -252,13 +265,22 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
         for (int i = 0; i < K + M; i++) crc_u[i] = fold(crc_u[i]);
       }
       const size_t tile_start = seg_start + (size_t)t * kBsTile;
+      // CRC: a thread owns 64 contiguous bytes per tile (its Horner register needs contiguity), so a
+      // warp's 256-bit load covers every other 32-byte sector of 2 KiB.  Without CRC the two groups of a
+      // warp are two contiguous 1 KiB runs: whole 128-byte lines per request.
+#ifndef CUBEEC_BS_GSTRIDE_OFF
+      const size_t col0 = CRC ? tile_start + (size_t)tid * kBsPiece : tile_start + (size_t)warp * (32 * kBsPiece) + (size_t)lane * 32;
+      constexpr size_t GSTRIDE = CRC ? 32 : 1024;
+#else
       const size_t col0 = tile_start + (size_t)tid * kBsPiece;
+      constexpr size_t GSTRIDE = 32;
+#endif
       if (tile_start + kBsTile <= p.shard_len) {
 #pragma unroll 1
-        for (int g = 0; g < kBsGroups; g++) group(std::true_type{}, sbase, col0 + (size_t)g * 32);
+        for (int g = 0; g < kBsGroups; g++) group(std::true_type{}, sbase, col0 + (size_t)g * GSTRIDE);
       } else {
 #pragma unroll 1
-        for (int g = 0; g < kBsGroups; g++) group(std::false_type{}, sbase, col0 + (size_t)g * 32);
+        for (int g = 0; g < kBsGroups; g++) group(std::false_type{}, sbase, col0 + (size_t)g * GSTRIDE);
       }
     }
 

