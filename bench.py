@@ -245,7 +245,7 @@ def main():
     ap.add_argument("--cpu-stripes", type=int, default=256, help="stripes in the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "table", "ws"],
+    ap.add_argument("--kernel", default="auto", choices=["auto", "table", "ws", "bsrec"],
                     help="A/B aid: table = generic table kernel, ws = warp-specialised fused encode+CRC kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -274,6 +274,8 @@ def main():
         cb.force_kernel(1)
     if args.kernel == "ws":
         cb.force_kernel(5)
+    if args.kernel == "bsrec":
+        cb.force_kernel(2)
 
     # coding matrix: built on rank 0, NCCL-broadcast to the other ranks (the only shared state)
     if rank == 0:

@@ -38,13 +38,13 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
   // ---- shared memory: [misc: mbarrier | fold tables (4 copies) | kthread | reduction] ... [64K-aligned slice image]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   uint32_t* fold_s = reinterpret_cast<uint32_t*>(smem + 64);                       // [4][256][kBsFoldCopies]
-  uint32_t* kth_s = fold_s + 4 * 256 * kBsFoldCopies;                              // [NT]
-  uint32_t* red_s = kth_s + NT;                                                    // [(K+M)][NW]
+  uint32_t* kth_s = fold_s + 4 * 256 * kBsFoldCopies;                              // [2][NT]: [1] = [0] * x^(8*tile)
+  uint32_t* red_s = kth_s + 2 * NT;                                                    // [(K+M)][NW]
   uint32_t* red2_s = red_s + (K + M) * NW;                                         // packed mode: [kBsPackedMaxStripes][(K+M)]
   const uint32_t base_addr = smem_addr(smem);
   uint32_t tab_addr = 0;   // shared address of the slice image
   if (CRC) {
-    tab_addr = (base_addr + (uint32_t)(64 + 4 * 256 * kBsFoldCopies * 4 + NT * 4 + (K + M) * NW * 4 + kBsPackedMaxStripes * (K + M) * 4) + 65535u) & ~65535u;
+    tab_addr = (base_addr + (uint32_t)(64 + 4 * 256 * kBsFoldCopies * 4 + 2 * NT * 4 + (K + M) * NW * 4 + kBsPackedMaxStripes * (K + M) * 4) + 65535u) & ~65535u;
     uint8_t* tab_ptr = smem + (tab_addr - base_addr);
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
       for (int q = 0; q < kBsFoldCopies; q++) fold_s[i * kBsFoldCopies + q] = v;
     }
     kth_s[tid] = p.kthread[tid];
+    kth_s[NT + tid] = p.kthread[NT + tid];
     uint32_t done = 0;
     while (!done) {
       asm volatile(
@@ -258,24 +259,30 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
     const uint32_t T = (seg == p.n_seg - 1) ? p.tiles_last : p.tiles_per_seg;
     const size_t seg_start = (size_t)seg * seg_bytes;
 
+    bool skipped_tile = false;   // warp-uniform: this warp's 2 KiB of the shard's final tile lie beyond shard_len
     for (uint32_t t = 0; t < T; t++) {
+      const size_t tile_start = seg_start + (size_t)t * kBsTile;
+      // Without CRC, FULL / ragged / nothing is decided per WARP (2 KiB of every shard), not per tile: in
+      // the final tile of a shard the warps inside run the unmasked path and the warps past the end do
+      // nothing.  (A CRC register that sits a tile out is realigned through kthread[NT + tid].)
+      // (fused-CRC variant: measured 1.6 % SLOWER with the per-warp decision -- it keeps the per-tile one)
+      const size_t warp_lo = tile_start + (size_t)warp * (32 * kBsPiece);
+      const bool warp_full = CRC ? tile_start + kBsTile <= p.shard_len : warp_lo + 32 * kBsPiece <= p.shard_len;
+      if (!CRC && warp_lo >= p.shard_len) {
+        skipped_tile = true;
+        continue;
+      }
       if (CRC) {
         // Horner step: skip the gap between the end of this thread's previous piece and this one
 #pragma unroll
         for (int i = 0; i < K + M; i++) crc_u[i] = fold(crc_u[i]);
       }
-      const size_t tile_start = seg_start + (size_t)t * kBsTile;
       // CRC: a thread owns 64 contiguous bytes per tile (its Horner register needs contiguity), so a
       // warp's 256-bit load covers every other 32-byte sector of 2 KiB.  Without CRC the two groups of a
       // warp are two contiguous 1 KiB runs: whole 128-byte lines per request.
-#ifndef CUBEEC_BS_GSTRIDE_OFF
-      const size_t col0 = CRC ? tile_start + (size_t)tid * kBsPiece : tile_start + (size_t)warp * (32 * kBsPiece) + (size_t)lane * 32;
+      const size_t col0 = CRC ? tile_start + (size_t)tid * kBsPiece : warp_lo + (size_t)lane * 32;
       constexpr size_t GSTRIDE = CRC ? 32 : 1024;
-#else
-      const size_t col0 = tile_start + (size_t)tid * kBsPiece;
-      constexpr size_t GSTRIDE = 32;
-#endif
-      if (tile_start + kBsTile <= p.shard_len) {
+      if (warp_full) {
 #pragma unroll 1
         for (int g = 0; g < kBsGroups; g++) group(std::true_type{}, sbase, col0 + (size_t)g * GSTRIDE);
       } else {
@@ -289,7 +296,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
       vdiff = 0;
     }
     if (CRC && p.crc_part) {
-      const uint32_t kt = kth_s[tid];
+      const uint32_t kt = kth_s[skipped_tile ? NT + tid : tid];
 #pragma unroll
       for (int q = 0; q < K + M; q++) {
         uint32_t u = gf32_mul_dev(crc_u[q], kt, p.poly);
@@ -487,13 +494,16 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bsrec_kernel(const BsRecPara
 
     for (uint32_t t = 0; t < T; t++) {
       const size_t tile_start = seg_start + (size_t)t * kBsTile;
-      const size_t col0 = tile_start + (size_t)tid * kBsPiece;
-      if (tile_start + kBsTile <= p.shard_len) {
+      // whole-line requests: the two groups of a warp are two contiguous 1 KiB runs (see rs_bs_kernel)
+      const size_t warp_lo = tile_start + (size_t)(tid >> 5) * (32 * kBsPiece);
+      if (warp_lo >= p.shard_len) continue;   // per-warp decision, as in rs_bs_kernel
+      const size_t col0 = warp_lo + (size_t)(tid & 31) * 32;
+      if (warp_lo + 32 * kBsPiece <= p.shard_len) {
 #pragma unroll 1
-        for (int g = 0; g < kBsGroups; g++) group(std::true_type{}, col0 + (size_t)g * 32);
+        for (int g = 0; g < kBsGroups; g++) group(std::true_type{}, col0 + (size_t)g * 1024);
       } else {
 #pragma unroll 1
-        for (int g = 0; g < kBsGroups; g++) group(std::false_type{}, col0 + (size_t)g * 32);
+        for (int g = 0; g < kBsGroups; g++) group(std::false_type{}, col0 + (size_t)g * 1024);
       }
     }
   }

@@ -144,8 +144,11 @@ int setup_device(DevCtx& c) {
         for (int l = 0; l < 32; l++) img[((size_t)(j >> 1) * 65536 + (size_t)v * 256 + (size_t)(j & 1) * 128) / 4 + l] = ct->slice[j][v];
     uint32_t fold[4][256];
     crc_const_mul_tables(P, P.shift_bytes_const((int64_t)kBsTile - kBsPiece), fold);
-    std::vector<uint32_t> kth(kBsThreads);
-    for (int t = 0; t < kBsThreads; t++) kth[t] = P.shift_bytes_const((int64_t)kBsTile - (int64_t)kBsPiece * (t + 1));
+    std::vector<uint32_t> kth(2 * kBsThreads);   // second half: the thread sat out the shard's final tile
+    for (int t = 0; t < kBsThreads; t++) {
+      kth[t] = P.shift_bytes_const((int64_t)kBsTile - (int64_t)kBsPiece * (t + 1));
+      kth[kBsThreads + t] = P.shift_bytes_const(2 * (int64_t)kBsTile - (int64_t)kBsPiece * (t + 1));
+    }
     CU(cudaMalloc(&c.d_bs_slice[pi], kBsSliceImageBytes));
     CU(cudaMemcpy(c.d_bs_slice[pi], img.data(), kBsSliceImageBytes, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c.d_bs_fold[pi], sizeof(fold)));
