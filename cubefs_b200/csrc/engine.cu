@@ -269,7 +269,7 @@ struct cubeec {
   std::vector<Pattern> verify_passes;
   std::vector<Pattern*> d_enc;      // per ctx: device copy [n_passes]
   std::vector<Pattern*> d_verify;   // same, crc_in = 0
-  bool bs_ok = false;               // a specialised bit-sliced network exists for this matrix
+  int bs_passes = 0;                // bit-sliced passes this matrix takes (bs_passes()); 0 = table kernels only
   // Batched-reconstruct plans: the pattern tables of a whole presence array, resident on a device,
   // so that repeating a repair batch costs no host-side matrix work or uploads.
   struct Plan {
@@ -566,7 +566,7 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
   const int n = h->k + h->m;
   const size_t ci = ctx_index(&c);
   const bool want_crc = mode == 0 && d_crc_out;
-  if (h->bs_ok && g_force_kernel.load() != 1 && bs_layout_ok(d_base, shard_len, shard_pitch, stripe_pitch)) {
+  if (h->bs_passes && g_force_kernel.load() != 1 && bs_layout_ok(d_base, shard_len, shard_pitch, stripe_pitch)) {
     // hot path: bit-sliced XOR-network kernel (bitslice.cu)
     Geometry gm = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
     // shards shorter than a tile: packed mode (pieces of many stripes share a tile)
@@ -574,7 +574,7 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
     const bool packed = pps < (uint32_t)kBsThreads && pps >= 8;
     // opt-in A/B aid: the warp-specialised fused kernel (bitslice_ws.cu; measured within +-3 % of
     // rs_bs_kernel<crc>, see DESIGN.md "issue ceiling")
-    const bool ws = want_crc && !packed && g_force_kernel.load() == 5 && bsw_supported(h->k, h->m);
+    const bool ws = want_crc && !packed && g_force_kernel.load() == 5 && h->bs_passes == 1 && bsw_supported(h->k, h->m);
     if (ws) gm = pick_geometry(c, shard_len, n_stripes, false, kBswTile);
     if (packed) {
       const uint64_t tiles = ((uint64_t)n_stripes * pps + kBsThreads - 1) / kBsThreads;
@@ -608,9 +608,16 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
     bp.poly = g.poly[pi].poly;
     bp.k65536 = 65536u;
     bp.packed_pps = gm.packed_pps;
-    if (ws) CU(launch_bsw(h->k, h->m, bp, gm.grid, stream));
-    else CU(launch_bs(h->k, h->m, bp, want_crc, mode == 1, gm.grid, stream));
-    g_launches++;
+    if (ws) {
+      CU(launch_bsw(h->k, h->m, bp, gm.grid, stream));
+      g_launches++;
+    } else {
+      // m > 4: one pass per group of 4 parity rows; the first also checksums the data shards
+      for (int pass = 0; pass < h->bs_passes; pass++) {
+        CU(launch_bs(h->k, h->m, pass, bp, want_crc ? (pass == 0 ? 1 : 2) : 0, mode == 1, gm.grid, stream));
+        g_launches++;
+      }
+    }
     t_last_kernel = ws ? "rs_bsw_kernel" : want_crc ? "rs_bs_kernel<crc>" : mode == 1 ? "rs_bs_kernel<verify>" : "rs_bs_kernel";
     if (want_crc) {
       int rc = finalize_crc(c, stream, d_part, n_stripes, n, shard_len, gm, crc_poly, nullptr, d_crc_out);
@@ -722,7 +729,7 @@ extern "C" int cubeec_create(int k, int m, const uint8_t* parity_rows, cubeec_t*
     make_passes(ins, outs, rows, false, h->verify_passes);
     rc = upload_handle_patterns(h.get());
     if (rc) return rc;
-    h->bs_ok = bs_supported(k, m, rows.data());
+    h->bs_passes = bs_passes(k, m, rows.data());
   }
   *out = h.release();
   return CUBEEC_OK;
@@ -854,7 +861,7 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
   }
   // The bit-sliced syndrome kernel is exact but (as measured, profiles/) still slower than the
   // fixed-arity table kernel on B200; it is opt-in (cubeec_debug_force_kernel(2)) until it wins.
-  const bool use_rec = h->bs_ok && h->m <= 4 && g_force_kernel.load() == 2 &&
+  const bool use_rec = h->bs_passes == 1 && bs_rec_supported(h->k, h->m) && g_force_kernel.load() == 2 &&
                        bs_layout_ok((const uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch);
   if (plan && use_rec != (plan->d_rec != nullptr)) plan = nullptr;
   std::unique_ptr<cubeec::Plan> fresh;

@@ -18,8 +18,13 @@ the handle's matrix equals the one the network was specialised for.
 """
 import sys
 
-# (k, m) with m <= 4: one pass, 8*m accumulator registers
-CONFIGS = [(4, 2), (6, 3), (12, 4), (20, 4), (16, 4), (10, 4), (3, 3), (4, 4), (8, 4), (6, 2), (10, 2), (5, 2)]
+# (k, m) with m <= 4: one pass, 8*m accumulator registers.  The second group are the local stripes of
+# the LRC code modes (codemode.go:72-73,83,86-88: RS((N+M)/AZ, L/AZ)).
+CONFIGS = [(4, 2), (6, 3), (12, 4), (20, 4), (16, 4), (10, 4), (3, 3), (4, 4), (8, 4), (6, 2), (10, 2), (5, 2),
+           (18, 1), (8, 1), (3, 1), (4, 1), (4, 3)]
+# (k, m) with m > 4 (EC15P12, EC6P6, EC16P20L2, EC6P10L2, EC12P9, EC24P8, EC6P8L10 and its local stripe):
+# passes of 4 parity rows, each pass re-reads the k data shards
+PASS_CONFIGS = [(15, 12), (6, 6), (16, 20), (6, 10), (12, 9), (24, 8), (6, 8), (7, 5)]
 
 
 def gf_tables():
@@ -144,30 +149,51 @@ def emit_shard(lines, coefs, var_p="p", var_acc="acc"):
     return n_xor3
 
 
+def emit_net(L, k, m, v, rows, mt, r0):
+    L.append(f"template <> struct BsNet<{k}, {m}, {v}> {{")
+    L.append(f"  static constexpr int K = {k}, M = {m}, kTotalM = {mt}, kRow0 = {r0};")
+    flat = ", ".join(str(x) for row in rows for x in row)
+    L.append(f"  static constexpr uint8_t kRows[{k * m}] = {{{flat}}};")
+    L.append("  // acc[r*8+i] ^= plane i of (rows[r][C] * shard C), shard C given as 8 bit-planes p[0..7]")
+    L.append("  template <int C> static __device__ __forceinline__ void apply(const uint32_t (&p)[8], uint32_t (&acc)[8 * M]) {")
+    for c in range(k):
+        L.append(f"    if constexpr (C == {c}) {{")
+        body = []
+        emit_shard(body, [rows[r][c] for r in range(m)])
+        L.extend("  " + ln for ln in body)
+        L.append("    }")
+    L.append("  }")
+    L.append("};")
+
+
+def pass_id(mt, r0):
+    """template tag of the pass that computes parity rows [r0, r0+4) of a code with mt > 4 parity shards"""
+    return mt * 100 + r0
+
+
 def main(out_path):
     L = []
     L.append("// GENERATED by gen_bitslice.py -- do not edit.  GF(2) XOR networks of the bit-sliced encode kernel.")
     L.append("#pragma once")
     L.append("#include <cstdint>")
     L.append("namespace cbe {")
-    L.append("template <int K, int M> struct BsNet;   // specialised below for the configurations in gen_bitslice.py")
+    L.append("// BsNet<K, M, 0>: all M <= 4 parity rows of RS(K, M).  BsNet<K, M, V>, V = 100*MT + R0: rows")
+    L.append("// [R0, R0+M) of RS(K, MT) with MT > 4 -- such codes run ceil(MT/4) passes over the data shards.")
+    L.append("template <int K, int M, int V = 0> struct BsNet;")
+    full, passes = [], []
     for (k, m) in CONFIGS:
-        rows = parity_rows(k, m)
-        L.append(f"template <> struct BsNet<{k}, {m}> {{")
-        L.append(f"  static constexpr int K = {k}, M = {m};")
-        flat = ", ".join(str(v) for row in rows for v in row)
-        L.append(f"  static constexpr uint8_t kRows[{k * m}] = {{{flat}}};")
-        L.append("  // acc[r*8+i] ^= plane i of (rows[r][C] * shard C), shard C given as 8 bit-planes p[0..7]")
-        L.append("  template <int C> static __device__ __forceinline__ void apply(const uint32_t (&p)[8], uint32_t (&acc)[8 * M]) {")
-        for c in range(k):
-            L.append(f"    if constexpr (C == {c}) {{")
-            body = []
-            emit_shard(body, [rows[r][c] for r in range(m)])
-            L.extend("  " + ln for ln in body)
-            L.append("    }")
-        L.append("  }")
-        L.append("};")
+        emit_net(L, k, m, 0, parity_rows(k, m), m, 0)
+        full.append(f"X({k}, {m})")
+    for (k, mt) in PASS_CONFIGS:
+        rows = parity_rows(k, mt)
+        for r0 in range(0, mt, 4):
+            m = min(4, mt - r0)
+            emit_net(L, k, m, pass_id(mt, r0), rows[r0:r0 + m], mt, r0)
+            passes.append(f"X({k}, {m}, {pass_id(mt, r0)}, {mt}, {r0})")
     L.append("}  // namespace cbe")
+    L.append("// X(K, M): single-pass configurations;  X(K, M, V, MT, R0): passes of the MT > 4 codes")
+    L.append("#define CUBEEC_BS_CONFIGS(X) " + " ".join(full))
+    L.append("#define CUBEEC_BS_PASS_CONFIGS(X) " + " ".join(passes))
     open(out_path, "w").write("\n".join(L) + "\n")
 
 

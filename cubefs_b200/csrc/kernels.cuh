@@ -178,9 +178,15 @@ struct BsRecParams {
   const GfDeviceTables* gf;
 };
 
-bool bs_supported(int k, int m, const uint8_t* parity_rows);   // a specialised network exists for this matrix
+// Number of bit-sliced passes RS(k, m) with these parity rows takes: 1 (m <= 4), ceil(m/4) for the
+// generated m > 4 codes, 0 = no specialised network (the table kernels serve it).
+int bs_passes(int k, int m, const uint8_t* parity_rows);
+int bs_mp_passes(int k, int m, const uint8_t* parity_rows);                     // bitslice_mp.cu
+bool bs_rec_supported(int k, int m);
 cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStream_t st);
-cudaError_t launch_bs(int k, int m, const BsParams& p, bool crc, bool verify, int grid, cudaStream_t st);
+// crc: 0 none, 1 all shards (pass 0), 2 the pass's outputs only (pass > 0)
+cudaError_t launch_bs(int k, int m, int pass, const BsParams& p, int crc, bool verify, int grid, cudaStream_t st);
+cudaError_t launch_bs_mp(int k, int m, int pass, const BsParams& p, int crc, bool verify, int grid, cudaStream_t st);
 bool bsw_supported(int k, int m);                              // bitslice_ws.cu has this configuration (and its register split is safe)
 cudaError_t launch_bsw(int k, int m, const BsParams& p, int grid, cudaStream_t st);
 
