@@ -41,7 +41,7 @@ def shard_size(blob, k, min_shard=2048):
 def measured_traffic(kernel: str, stripes: int):
     """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the ncu --set full
     capture summarised under profiles/ (taken at 1024 stripes; scaled linearly to this batch)."""
-    name = {"rs_bsw_kernel": "r01_prof_bsw.txt", "rs_bs_kernel<crc>": "r01_prof_r1_bs_crc.txt", "rs_bs_kernel": "r01_prof_r1_bs_nocrc.txt",
+    name = {"rs_bs_kernel<crc>": "r01_prof_r1_bs_crc.txt", "rs_bs_kernel": "r01_prof_r1_bs_nocrc.txt",
             "rs_tabk_kernel": "r01_prof_tabk_rec.txt"}.get(kernel)
     try:
         txt = open(os.path.join(ROOT, "profiles", name)).read()

@@ -51,6 +51,9 @@ def main():
     ap.add_argument("--gpu", type=int, default=0)
     ap.add_argument("--crc", type=int, default=1)
     ap.add_argument("--gib", type=float, default=2.0, help="batch size per case (GiB in HBM)")
+    ap.add_argument("--modes", action="store_true",
+                    help="instead of the C4/C5 shard-size sweep: every predefined EC code mode (codemode.go:65-94) at "
+                         "1 MiB shards, bit-sliced path and (A/B) the table kernels")
     args = ap.parse_args()
     dev = torch.device("cuda", args.gpu)
     torch.cuda.set_device(dev)
@@ -59,11 +62,19 @@ def main():
     cases = [(6, 3, s) for s in (4096, 16384, 65536, 262144, 1 << 20, 4 << 20, 8 << 20)]
     cases += [(12, 4, s) for s in (4096, 16384, 65536, 262144, 349526, 1 << 20, 4 << 20, 8 << 20)]
     cases += [(20, 4, 1 << 20), (4, 2, 65536)]
+    forces = [0]
+    if args.modes:
+        # global RS(N, M) of every predefined mode; m > 4 runs ceil(m/4) passes
+        cases = [(k, m, 1 << 20) for (k, m) in ((15, 12), (6, 6), (16, 20), (6, 10), (6, 3), (4, 4), (12, 4), (16, 4), (3, 3),
+                                                 (10, 4), (12, 9), (24, 8), (6, 8))]
+        forces = [0, 1]
     engines = {}
-    for (k, m, S) in cases:
+    for (k, m, S), force in [(c, f) for c in cases for f in forces]:
         eng = engines.setdefault((k, m), cb.RSEngine(k, m))
         for crc in ([0, 1] if args.crc else [0]):
+            cb.force_kernel(force)
             ns, ms, kern = run(eng, k, m, S, crc, args.gib * (1 << 30), dev)
+            cb.force_kernel(0)
             moved = (k + m) * S * ns / (ms * 1e-3) / 1e9
             print(json.dumps({"k": k, "m": m, "shard_bytes": S, "stripes": ns, "crc": bool(crc), "kernel": kern,
                               "ms": round(ms, 4), "data_GiB_s": round(k * S * ns / (ms * 1e-3) / 2**30, 1),
