@@ -61,15 +61,20 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-// table lookup address = base + 256 * (byte B of w) in ONE instruction on the FMA pipe: IDP.2A (dp2a)
+// table lookup address = base + STRIDE * (byte B of w) in ONE instruction on the FMA pipe: IDP.2A (dp2a)
 // multiplies the 16-bit halves of its first operand with two bytes of w (.lo: bytes 0,1; .hi: 2,3).
-template <int B>
+//
+// Product-table layout: entry (input c, byte value v, copy g) at  c*256*4R + v*4R + g*4  (R copies, copy
+// = lane % R).  The bank is then (v*R + g) mod 32 = g + R*(v mod 32/R): lanes that share a copy collide
+// only when their bytes agree modulo 32/R (R = 16: the low bit) -- 1.5 wavefronts per lookup instead of
+// the 2.0 of a layout whose bank does not depend on v.
+template <int B, uint32_t STRIDE>
 __device__ __forceinline__ uint32_t row_addr_b(uint32_t w, uint32_t base) {
   uint32_t d;
-  if (B == 0) asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(256u), "r"(w), "r"(base));
-  if (B == 1) asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(256u << 16), "r"(w), "r"(base));
-  if (B == 2) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(256u), "r"(w), "r"(base));
-  if (B == 3) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(256u << 16), "r"(w), "r"(base));
+  if (B == 0) asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(STRIDE), "r"(w), "r"(base));
+  if (B == 1) asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(STRIDE << 16), "r"(w), "r"(base));
+  if (B == 2) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(STRIDE), "r"(w), "r"(base));
+  if (B == 3) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(STRIDE << 16), "r"(w), "r"(base));
   return d;
 }
 
@@ -180,8 +185,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tab_kernel(const TabParams 
     off += (size_t)n_crc_slots * NW * 4;
     off = (off + 127) & ~(size_t)127;
   }
-  constexpr int SPR = 64 / R;                                 // shards per 256-byte table row
-  uint8_t* tab = smem + off;                                   // [ceil(n_in/SPR)][256 rows][SPR][R] u32
+  uint8_t* tab = smem + off;                                   // [n_in][256 values][R copies] u32 (see row_addr_b)
   const uint32_t tab_s = smem_u32(tab);
 
   const int tid = threadIdx.x;
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tab_kernel(const TabParams 
             if (co) e |= (uint32_t)gf_s->exp[gf_s->log[co] + lv] << (8 * r);
           }
         }
-        uint32_t* row = reinterpret_cast<uint32_t*>(tab + (size_t)(c / SPR) * 65536 + (size_t)v * 256 + (size_t)(c % SPR) * (4 * R));
+        uint32_t* row = reinterpret_cast<uint32_t*>(tab + (size_t)c * (1024 * R) + (size_t)v * (4 * R));
 #pragma unroll
         for (int q = 0; q < R; q++) row[q] = e;
       }
@@ -269,14 +273,14 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tab_kernel(const TabParams 
             uint4 dd = cur[i];
             if (tail) dd = keep_head(dd, tail);
             const int cc = c0 + i;
-            const uint32_t tb = tab_s + (uint32_t)(cc / SPR) * 65536u + (uint32_t)((cc % SPR) * (4 * R) + g * 4);
+            const uint32_t tb = tab_s + (uint32_t)cc * (1024u * R) + (uint32_t)(g * 4);
             const uint32_t w[4] = {dd.x, dd.y, dd.z, dd.w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-              acc[q * 4 + 0] ^= lds_u32(row_addr_b<0>(w[q], tb));
-              acc[q * 4 + 1] ^= lds_u32(row_addr_b<1>(w[q], tb));
-              acc[q * 4 + 2] ^= lds_u32(row_addr_b<2>(w[q], tb));
-              acc[q * 4 + 3] ^= lds_u32(row_addr_b<3>(w[q], tb));
+              acc[q * 4 + 0] ^= lds_u32(row_addr_b<0, 4 * R>(w[q], tb));
+              acc[q * 4 + 1] ^= lds_u32(row_addr_b<1, 4 * R>(w[q], tb));
+              acc[q * 4 + 2] ^= lds_u32(row_addr_b<2, 4 * R>(w[q], tb));
+              acc[q * 4 + 3] ^= lds_u32(row_addr_b<3, 4 * R>(w[q], tb));
             }
             if (crc_in) {
               uint32_t* st = crc_st + (size_t)cc * NT + tid;
@@ -347,7 +351,6 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tab_kernel(const TabParams 
 template <int R, int KF>
 __global__ void __launch_bounds__(kTabThreads, 1) rs_tabk_kernel(const TabParams p) {
   constexpr int NT = kTabThreads;
-  constexpr int SPR = 64 / R;
   constexpr int CH = KF <= 12 ? KF : (KF + 1) / 2;     // inputs loaded per chunk
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -391,7 +394,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tabk_kernel(const TabParams
             if (co) e |= (uint32_t)gf_s->exp[gf_s->log[co] + lv] << (8 * r);
           }
         }
-        uint32_t* row = reinterpret_cast<uint32_t*>(tab + (size_t)(c / SPR) * 65536 + (size_t)v * 256 + (size_t)(c % SPR) * (4 * R));
+        uint32_t* row = reinterpret_cast<uint32_t*>(tab + (size_t)c * (1024 * R) + (size_t)v * (4 * R));
 #pragma unroll
         for (int q = 0; q < R; q++) row[q] = e;
       }
@@ -433,23 +436,23 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tabk_kernel(const TabParams
           const int ca = c0 + i, cb = c0 + i + 1;
           if (ca < KF) {
             const bool two = (i + 1 < CH) && (cb < KF);
-            const uint32_t ta = tab_s + (uint32_t)(ca / SPR) * 65536u + (uint32_t)((ca % SPR) * (4 * R) + g * 4);
-            const uint32_t tb = tab_s + (uint32_t)((two ? cb : ca) / SPR) * 65536u + (uint32_t)(((two ? cb : ca) % SPR) * (4 * R) + g * 4);
+            const uint32_t ta = tab_s + (uint32_t)ca * (1024u * R) + (uint32_t)(g * 4);
+            const uint32_t tb = tab_s + (uint32_t)(two ? cb : ca) * (1024u * R) + (uint32_t)(g * 4);
             const uint32_t wa[4] = {d[i].x, d[i].y, d[i].z, d[i].w};
             const uint4 db = d[two ? i + 1 : i];
             const uint32_t wb[4] = {db.x, db.y, db.z, db.w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
               if (two) {
-                acc[q * 4 + 0] ^= lds_u32(row_addr_b<0>(wa[q], ta)) ^ lds_u32(row_addr_b<0>(wb[q], tb));
-                acc[q * 4 + 1] ^= lds_u32(row_addr_b<1>(wa[q], ta)) ^ lds_u32(row_addr_b<1>(wb[q], tb));
-                acc[q * 4 + 2] ^= lds_u32(row_addr_b<2>(wa[q], ta)) ^ lds_u32(row_addr_b<2>(wb[q], tb));
-                acc[q * 4 + 3] ^= lds_u32(row_addr_b<3>(wa[q], ta)) ^ lds_u32(row_addr_b<3>(wb[q], tb));
+                acc[q * 4 + 0] ^= lds_u32(row_addr_b<0, 4 * R>(wa[q], ta)) ^ lds_u32(row_addr_b<0, 4 * R>(wb[q], tb));
+                acc[q * 4 + 1] ^= lds_u32(row_addr_b<1, 4 * R>(wa[q], ta)) ^ lds_u32(row_addr_b<1, 4 * R>(wb[q], tb));
+                acc[q * 4 + 2] ^= lds_u32(row_addr_b<2, 4 * R>(wa[q], ta)) ^ lds_u32(row_addr_b<2, 4 * R>(wb[q], tb));
+                acc[q * 4 + 3] ^= lds_u32(row_addr_b<3, 4 * R>(wa[q], ta)) ^ lds_u32(row_addr_b<3, 4 * R>(wb[q], tb));
               } else {
-                acc[q * 4 + 0] ^= lds_u32(row_addr_b<0>(wa[q], ta));
-                acc[q * 4 + 1] ^= lds_u32(row_addr_b<1>(wa[q], ta));
-                acc[q * 4 + 2] ^= lds_u32(row_addr_b<2>(wa[q], ta));
-                acc[q * 4 + 3] ^= lds_u32(row_addr_b<3>(wa[q], ta));
+                acc[q * 4 + 0] ^= lds_u32(row_addr_b<0, 4 * R>(wa[q], ta));
+                acc[q * 4 + 1] ^= lds_u32(row_addr_b<1, 4 * R>(wa[q], ta));
+                acc[q * 4 + 2] ^= lds_u32(row_addr_b<2, 4 * R>(wa[q], ta));
+                acc[q * 4 + 3] ^= lds_u32(row_addr_b<3, 4 * R>(wa[q], ta));
               }
             }
           }
@@ -479,8 +482,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) rs_tabk_kernel(const TabParams
 }
 
 static size_t tabk_smem_bytes(int kf, int R) {
-  const int spr = 64 / R;
-  return ((16 + sizeof(GfDeviceTables) + sizeof(Pattern) + 127) & ~(size_t)127) + (size_t)((kf + spr - 1) / spr) * 65536;
+  return ((16 + sizeof(GfDeviceTables) + sizeof(Pattern) + 127) & ~(size_t)127) + (size_t)kf * 1024 * R;
 }
 
 template <int R, int KF>
@@ -517,8 +519,7 @@ static size_t tab_smem_bytes(int n_in, int R, bool with_crc, int n_crc_slots) {
     off += (size_t)n_crc_slots * (kTabThreads / 32) * 4;
     off = (off + 127) & ~(size_t)127;
   }
-  const int spr = 64 / R;
-  off += (size_t)((n_in + spr - 1) / spr) * 65536;
+  off += (size_t)n_in * 1024 * R;
   return off;
 }
 
