@@ -223,12 +223,12 @@ static cudaError_t launch_rec_cfg(const BsRecParams& p, int grid, cudaStream_t s
 // syndrome-reconstruct kernels exist for the code modes with 2 <= m <= 4
 #define CUBEEC_BSREC_CONFIGS(X) X(4, 2) X(6, 3) X(12, 4) X(20, 4) X(16, 4) X(10, 4) X(3, 3) X(4, 4) X(8, 4) X(6, 2) X(10, 2) X(5, 2)
 
-int bs_passes(int k, int m, const uint8_t* parity_rows) {
+int bs_passes(int k, int m, const uint8_t* parity_rows, int plan) {
 #define X(KK, MM) \
   if (k == KK && m == MM) return bs_rows_match<KK, MM, 0>(parity_rows) ? 1 : 0;
   CUBEEC_BS_CONFIGS(X)
 #undef X
-  return bs_mp_passes(k, m, parity_rows);
+  return bs_mp_passes(k, m, parity_rows, plan);
 }
 
 bool bs_rec_supported(int k, int m) {
@@ -248,8 +248,9 @@ cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStre
 }
 
 cudaError_t launch_bs(int k, int m, int pass, const BsParams& p, int crc, bool verify, int grid, cudaStream_t st) {
+  // single-pass codes serve every variant; the m > 4 codes have a pass plan per variant (bitslice_mp.cu)
 #define X(KK, MM) \
-  if (k == KK && m == MM) return pass == 0 ? bs_launch_cfg<KK, MM, 0>(p, crc, verify, grid, st) : cudaErrorInvalidValue;
+  if (k == KK && m == MM) return pass == 0 ? bs_launch_cfg<KK, MM, 0, 3>(p, crc, verify, grid, st) : cudaErrorInvalidValue;
   CUBEEC_BS_CONFIGS(X)
 #undef X
   return launch_bs_mp(k, m, pass, p, crc, verify, grid, st);

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
     // Look-ahead ring: DEPTH 256-bit loads per thread in flight ahead of the shard being coded.
     // The fused-CRC variant is ALU/issue bound and out of registers (DEPTH 1); the plain variant is
     // latency bound and uses its spare registers for a deep ring.
-    constexpr int DEPTH = CRC ? 1 : 4;
+    constexpr int DEPTH = CRC ? 1 : (M > 6 ? 1 : (M > 4 ? 2 : 4));   // wide passes (M > 4) need the registers for accumulators
     uint32_t ring[DEPTH + 1][8];
 #pragma unroll
     for (int b = 0; b <= DEPTH; b++)
@@ -319,26 +319,37 @@ static bool bs_rows_match(const uint8_t* rows /* [kTotalM][K] of the handle */) 
   return true;
 }
 
-// crc: 0 none, 1 all shards, 2 outputs only.  Only the CRC modes a network can be asked for are
-// instantiated: single-pass codes and first passes checksum everything, later passes their outputs.
-template <int K, int M, int V>
+// crc: 0 none, 1 all shards, 2 outputs only.  Only the variants a network can be asked for are
+// instantiated: WHAT = 3 everything (single-pass codes), 1 fused-CRC plan passes (first pass checksums
+// everything, later passes their outputs), 2 plain plan passes (encode without CRC, verify).
+template <int K, int M, int V, int WHAT>
 static cudaError_t bs_launch_cfg(const BsParams& p, int crc, bool verify, int grid, cudaStream_t st) {
   using Net = BsNet<K, M, V>;
   constexpr int MODE = Net::kRow0 == 0 ? 1 : 2;
   cudaError_t e;
   const bool packed = p.packed_pps != 0;
   if (crc) {
-    if (verify || crc != MODE) return cudaErrorInvalidValue;
-    auto kern = packed ? rs_bs_kernel<K, M, V, MODE, true> : rs_bs_kernel<K, M, V, MODE, false>;
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsSmemBytes)) != cudaSuccess) return e;
-    kern<<<grid, kBsThreads, kBsSmemBytes, st>>>(p);
-  } else if (verify) {
-    if (packed) rs_bs_kernel<K, M, V, 0, true, true><<<grid, kBsThreads, 4096, st>>>(p);
-    else rs_bs_kernel<K, M, V, 0, false, true><<<grid, kBsThreads, 4096, st>>>(p);
-  } else if (packed) {
-    rs_bs_kernel<K, M, V, 0, true><<<grid, kBsThreads, 4096, st>>>(p);
+    if constexpr ((WHAT & 1) != 0) {
+      if (verify || crc != MODE) return cudaErrorInvalidValue;
+      auto kern = packed ? rs_bs_kernel<K, M, V, MODE, true> : rs_bs_kernel<K, M, V, MODE, false>;
+      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsSmemBytes)) != cudaSuccess) return e;
+      kern<<<grid, kBsThreads, kBsSmemBytes, st>>>(p);
+    } else {
+      return cudaErrorInvalidValue;
+    }
   } else {
-    rs_bs_kernel<K, M, V, 0, false><<<grid, kBsThreads, 4096, st>>>(p);
+    if constexpr ((WHAT & 2) != 0) {
+      if (verify) {
+        if (packed) rs_bs_kernel<K, M, V, 0, true, true><<<grid, kBsThreads, 4096, st>>>(p);
+        else rs_bs_kernel<K, M, V, 0, false, true><<<grid, kBsThreads, 4096, st>>>(p);
+      } else if (packed) {
+        rs_bs_kernel<K, M, V, 0, true><<<grid, kBsThreads, 4096, st>>>(p);
+      } else {
+        rs_bs_kernel<K, M, V, 0, false><<<grid, kBsThreads, 4096, st>>>(p);
+      }
+    } else {
+      return cudaErrorInvalidValue;
+    }
   }
   return cudaGetLastError();
 }

@@ -269,7 +269,8 @@ struct cubeec {
   std::vector<Pattern> verify_passes;
   std::vector<Pattern*> d_enc;      // per ctx: device copy [n_passes]
   std::vector<Pattern*> d_verify;   // same, crc_in = 0
-  int bs_passes = 0;                // bit-sliced passes this matrix takes (bs_passes()); 0 = table kernels only
+  int bs_passes = 0;                // bit-sliced passes with fused CRC (bs_passes() plan 0); 0 = table kernels only
+  int bs_passes_plain = 0;          // ... of a plain encode / verify (plan 1: wider passes)
   // Batched-reconstruct plans: the pattern tables of a whole presence array, resident on a device,
   // so that repeating a repair batch costs no host-side matrix work or uploads.
   struct Plan {
@@ -613,7 +614,8 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
       g_launches++;
     } else {
       // m > 4: one pass per group of 4 parity rows; the first also checksums the data shards
-      for (int pass = 0; pass < h->bs_passes; pass++) {
+      const int n_pass = want_crc ? h->bs_passes : h->bs_passes_plain;
+      for (int pass = 0; pass < n_pass; pass++) {
         CU(launch_bs(h->k, h->m, pass, bp, want_crc ? (pass == 0 ? 1 : 2) : 0, mode == 1, gm.grid, stream));
         g_launches++;
       }
@@ -729,7 +731,9 @@ extern "C" int cubeec_create(int k, int m, const uint8_t* parity_rows, cubeec_t*
     make_passes(ins, outs, rows, false, h->verify_passes);
     rc = upload_handle_patterns(h.get());
     if (rc) return rc;
-    h->bs_passes = bs_passes(k, m, rows.data());
+    h->bs_passes = bs_passes(k, m, rows.data(), 0);
+    h->bs_passes_plain = bs_passes(k, m, rows.data(), 1);
+    if (!h->bs_passes || !h->bs_passes_plain) h->bs_passes = h->bs_passes_plain = 0;
   }
   *out = h.release();
   return CUBEEC_OK;

@@ -166,9 +166,28 @@ def emit_net(L, k, m, v, rows, mt, r0):
     L.append("};")
 
 
-def pass_id(mt, r0):
-    """template tag of the pass that computes parity rows [r0, r0+4) of a code with mt > 4 parity shards"""
-    return mt * 100 + r0
+def pass_split(mt, width):
+    """(first row, rows) of every pass of a code with mt > 4 parity shards: ceil(mt/width) passes of
+    balanced size (8 rows -> 4+4 rather than 6+2: a 2-row pass re-reads all the data for little)"""
+    n = -(-mt // width)
+    base, extra = divmod(mt, n)
+    out, r0 = [], 0
+    for i in range(n):
+        m = base + (1 if i < extra else 0)
+        out.append((r0, m))
+        r0 += m
+    return out
+
+
+# Two pass plans per code.  Plan 0 (fused CRC): 4 rows per pass -- the first pass also carries the k CRC
+# registers of the data shards.  Plan 1 (plain encode / verify): 6 rows per pass (48 accumulator
+# registers, no spills at 128 registers/thread), e.g. EC15P12 reads the data twice instead of 3 times.
+PLAN_WIDTH = (4, 6)
+
+
+def pass_id(mt, r0, plan):
+    """template tag of the pass that computes parity rows [r0, ...) of a code with mt > 4 parity shards"""
+    return plan * 10000 + mt * 100 + r0
 
 
 def main(out_path):
@@ -177,8 +196,8 @@ def main(out_path):
     L.append("#pragma once")
     L.append("#include <cstdint>")
     L.append("namespace cbe {")
-    L.append("// BsNet<K, M, 0>: all M <= 4 parity rows of RS(K, M).  BsNet<K, M, V>, V = 100*MT + R0: rows")
-    L.append("// [R0, R0+M) of RS(K, MT) with MT > 4 -- such codes run ceil(MT/4) passes over the data shards.")
+    L.append("// BsNet<K, M, 0>: all M <= 4 parity rows of RS(K, M).  BsNet<K, M, V>, V = 10000*PLAN + 100*MT + R0:")
+    L.append("// rows [R0, R0+M) of RS(K, MT) with MT > 4 -- such codes run several passes over the data shards.")
     L.append("template <int K, int M, int V = 0> struct BsNet;")
     full, passes = [], []
     for (k, m) in CONFIGS:
@@ -186,12 +205,12 @@ def main(out_path):
         full.append(f"X({k}, {m})")
     for (k, mt) in PASS_CONFIGS:
         rows = parity_rows(k, mt)
-        for r0 in range(0, mt, 4):
-            m = min(4, mt - r0)
-            emit_net(L, k, m, pass_id(mt, r0), rows[r0:r0 + m], mt, r0)
-            passes.append(f"X({k}, {m}, {pass_id(mt, r0)}, {mt}, {r0})")
+        for plan, width in enumerate(PLAN_WIDTH):
+            for pi, (r0, m) in enumerate(pass_split(mt, width)):
+                emit_net(L, k, m, pass_id(mt, r0, plan), rows[r0:r0 + m], mt, r0)
+                passes.append(f"X({k}, {m}, {pass_id(mt, r0, plan)}, {mt}, {r0}, {pi}, {plan})")
     L.append("}  // namespace cbe")
-    L.append("// X(K, M): single-pass configurations;  X(K, M, V, MT, R0): passes of the MT > 4 codes")
+    L.append("// X(K, M): single-pass configurations;  X(K, M, V, MT, R0, PASS, PLAN): passes of the MT > 4 codes (plan 0: fused CRC, plan 1: plain/verify)")
     L.append("#define CUBEEC_BS_CONFIGS(X) " + " ".join(full))
     L.append("#define CUBEEC_BS_PASS_CONFIGS(X) " + " ".join(passes))
     open(out_path, "w").write("\n".join(L) + "\n")

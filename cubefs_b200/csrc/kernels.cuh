@@ -178,10 +178,11 @@ struct BsRecParams {
   const GfDeviceTables* gf;
 };
 
-// Number of bit-sliced passes RS(k, m) with these parity rows takes: 1 (m <= 4), ceil(m/4) for the
-// generated m > 4 codes, 0 = no specialised network (the table kernels serve it).
-int bs_passes(int k, int m, const uint8_t* parity_rows);
-int bs_mp_passes(int k, int m, const uint8_t* parity_rows);                     // bitslice_mp.cu
+// Number of bit-sliced passes RS(k, m) with these parity rows takes: 1 (m <= 4); for the generated
+// m > 4 codes ceil(m/4) with fused CRC (plan 0) or ceil(m/6) without (plan 1); 0 = no specialised
+// network (the table kernels serve it).
+int bs_passes(int k, int m, const uint8_t* parity_rows, int plan);
+int bs_mp_passes(int k, int m, const uint8_t* parity_rows, int plan);           // bitslice_mp.cu
 bool bs_rec_supported(int k, int m);
 cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStream_t st);
 // crc: 0 none, 1 all shards (pass 0), 2 the pass's outputs only (pass > 0)
