@@ -10,5 +10,5 @@ package is the Python host-side binding used by tests and bench.py:
 
 There is no CPU compute path: importing works anywhere, calling needs a CUDA device.
 """
-from .engine import (CubeecError, RSEngine, crc32, crc32_blocks, device_count, force_kernel, init,  # noqa: F401
-                     kernel_launches, last_kernel, lib_path, load)
+from .engine import (CubeecError, RSEngine, crc32, crc32_blocks, dev_lrc_encode, device_count, force_kernel,  # noqa: F401
+                     init, kernel_launches, last_kernel, lib_path, load, lrc_encode_contig)

@@ -249,8 +249,10 @@ cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStre
 
 cudaError_t launch_bs(int k, int m, int pass, const BsParams& p, int crc, bool verify, int grid, cudaStream_t st) {
   // single-pass codes serve every variant; the m > 4 codes have a pass plan per variant (bitslice_mp.cu)
+  // outputs-only CRC (4) exists for the LRC local-stripe codes
 #define X(KK, MM) \
-  if (k == KK && m == MM) return pass == 0 ? bs_launch_cfg<KK, MM, 0, 3>(p, crc, verify, grid, st) : cudaErrorInvalidValue;
+  if (k == KK && m == MM)   \
+    return pass == 0 ? bs_launch_cfg<KK, MM, 0, (MM == 1 || (KK == 4 && MM == 3)) ? 7 : 3>(p, crc, verify, grid, st) : cudaErrorInvalidValue;
   CUBEEC_BS_CONFIGS(X)
 #undef X
   return launch_bs_mp(k, m, pass, p, crc, verify, grid, st);

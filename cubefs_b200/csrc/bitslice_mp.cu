@@ -22,10 +22,23 @@ int bs_mp_passes(int k, int m, const uint8_t* parity_rows, int plan) {
   return ok ? n : 0;
 }
 
+// rows [*r0, *r0 + *rows) of the generator that pass `pass` of plan `plan` computes; false if there is none
+bool bs_mp_pass_rows(int k, int m, int plan, int pass, int* r0, int* rows) {
+#define X(KK, MM, VV, MT, RR, PP, PL)                        \
+  if (k == KK && m == MT && pass == PP && plan == PL) {      \
+    *r0 = RR;                                                \
+    *rows = MM;                                              \
+    return true;                                             \
+  }
+  CUBEEC_BS_PASS_CONFIGS(X)
+#undef X
+  return false;
+}
+
 cudaError_t launch_bs_mp(int k, int m, int pass, const BsParams& p, int crc, bool verify, int grid, cudaStream_t st) {
   const int plan = crc ? 0 : 1;
 #define X(KK, MM, VV, MT, RR, PP, PL)                                                                  \
-  if (k == KK && m == MT && pass == PP && plan == PL) return bs_launch_cfg<KK, MM, VV, PL == 0 ? 1 : 2>(p, crc, verify, grid, st);
+  if (k == KK && m == MT && pass == PP && plan == PL) return bs_launch_cfg<KK, MM, VV, PL == 1 ? 2 : (RR == 0 ? 5 : 4)>(p, crc, verify, grid, st);
   CUBEEC_BS_PASS_CONFIGS(X)
 #undef X
   return cudaErrorInvalidValue;

@@ -15,14 +15,15 @@ using namespace bsdev;
 // VERIFY (reedSolomon.Verify / checkSomeShards, RS/reedsolomon.go:770-784,1287-1301): the computed
 // parity is compared with the stored parity instead of being written; any difference raises the
 // stripe's flag in p.mismatch.  The reference allocates m scratch shards and runs bytes.Equal.
-// CRC: 0 = none, 1 = every shard, 2 = the M outputs only (later passes of an MT > 4 code: the data
-// shards were checksummed by the first pass).  V selects the network (bs_net_gen.cuh): 0 = RS(K, M),
-// else rows [kRow0, kRow0+M) of RS(K, kTotalM); outputs then go to slots K + kRow0 + r.
+// CRC: 0 = none, 1 = every shard, 2 = the M outputs only (later passes of an MT > 4 code and LRC local
+// stripes: the inputs were checksummed by an earlier pass).  V selects the network (bs_net_gen.cuh):
+// 0 = RS(K, M), else rows [kRow0, kRow0+M) of RS(K, kTotalM).  Which shard of the stripe input c / output
+// r is comes from p.in_slot / p.out_slot (identity + kRow0 for a plain code; the AZ's shard list for an
+// LRC local stripe, codemode.GetECLayoutByAZ).
 template <int K, int M, int V, int CRC, bool PACKED, bool VERIFY = false>
 __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) {
   static_assert(!(CRC && VERIFY), "verify does not checksum");
   using Net = BsNet<K, M, V>;
-  constexpr int R0 = Net::kRow0;            // first parity row of this pass
   constexpr int C0 = CRC == 2 ? K : 0;      // first checksummed shard (local index)
   constexpr int NT = kBsThreads, NW = NT / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -150,10 +151,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
     };
 #pragma unroll
     for (int c = 0; c < DEPTH && c < K; c++)
-      if (live) ldg256(src + (size_t)c * p.shard_pitch, ring[c % (DEPTH + 1)]);
+      if (live) ldg256(src + (size_t)p.in_slot[c] * p.shard_pitch, ring[c % (DEPTH + 1)]);
 #pragma unroll
     for (int c = 0; c < K; c++) {
-      if (c + DEPTH < K && live) ldg256(src + (size_t)(c + DEPTH) * p.shard_pitch, ring[(c + DEPTH) % (DEPTH + 1)]);
+      if (c + DEPTH < K && live) ldg256(src + (size_t)p.in_slot[c + DEPTH] * p.shard_pitch, ring[(c + DEPTH) % (DEPTH + 1)]);
       shard(c, ring[c % (DEPTH + 1)]);
     }
 #pragma unroll
@@ -165,12 +166,12 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
       if (VERIFY) {
         if (live) {
           uint32_t e[8];
-          ldg256(sbase + (size_t)(K + R0 + r) * p.shard_pitch + col, e);
+          ldg256(sbase + (size_t)p.out_slot[r] * p.shard_pitch + col, e);
 #pragma unroll
           for (int i = 0; i < 8; i++) vdiff |= o[i] ^ (FULL ? e[i] : (e[i] & msk[i]));
         }
       } else if (live) {
-        stg256(sbase + (size_t)(K + R0 + r) * p.shard_pitch + col, o);
+        stg256(sbase + (size_t)p.out_slot[r] * p.shard_pitch + col, o);
       }
       if (CRC) {
         uint32_t u = crc_u[K + r];
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
         for (uint32_t i = tid; i < nstr * (K + M); i += NT) {
           const uint32_t sj = stripe0 + i / (K + M), q = i % (K + M);
           const uint32_t segidx = tile - (uint32_t)(((uint64_t)sj * PPS) / NT);   // 0 or 1: a shard spans at most two tiles
-          if (q >= (uint32_t)C0) p.crc_part[((size_t)sj * p.n_slots + (q < (uint32_t)K ? q : q + R0)) * 2 + segidx] = red2_s[i];
+          if (q >= (uint32_t)C0) p.crc_part[((size_t)sj * p.n_slots + (q < (uint32_t)K ? p.in_slot[q] : p.out_slot[q - K])) * 2 + segidx] = red2_s[i];
         }
         __syncthreads();
       }
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
         uint32_t u = 0;
 #pragma unroll
         for (int w2 = 0; w2 < NW; w2++) u ^= red_s[tid * NW + w2];
-        p.crc_part[((size_t)s * p.n_slots + (tid < K ? tid : tid + R0)) * p.n_seg + seg] = u;
+        p.crc_part[((size_t)s * p.n_slots + (tid < K ? p.in_slot[tid] : p.out_slot[tid - K])) * p.n_seg + seg] = u;
       }
       __syncthreads();
     }
@@ -320,38 +321,41 @@ static bool bs_rows_match(const uint8_t* rows /* [kTotalM][K] of the handle */) 
 }
 
 // crc: 0 none, 1 all shards, 2 outputs only.  Only the variants a network can be asked for are
-// instantiated: WHAT = 3 everything (single-pass codes), 1 fused-CRC plan passes (first pass checksums
-// everything, later passes their outputs), 2 plain plan passes (encode without CRC, verify).
+// instantiated, WHAT = OR of: 1 fused CRC of every shard, 2 plain encode + verify, 4 fused CRC of the
+// outputs only.
+template <int K, int M, int V, int MODE>
+static cudaError_t bs_launch_crc(const BsParams& p, int grid, cudaStream_t st) {
+  auto kern = p.packed_pps != 0 ? rs_bs_kernel<K, M, V, MODE, true> : rs_bs_kernel<K, M, V, MODE, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsSmemBytes);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kBsThreads, kBsSmemBytes, st>>>(p);
+  return cudaGetLastError();
+}
+
 template <int K, int M, int V, int WHAT>
 static cudaError_t bs_launch_cfg(const BsParams& p, int crc, bool verify, int grid, cudaStream_t st) {
-  using Net = BsNet<K, M, V>;
-  constexpr int MODE = Net::kRow0 == 0 ? 1 : 2;
-  cudaError_t e;
   const bool packed = p.packed_pps != 0;
-  if (crc) {
-    if constexpr ((WHAT & 1) != 0) {
-      if (verify || crc != MODE) return cudaErrorInvalidValue;
-      auto kern = packed ? rs_bs_kernel<K, M, V, MODE, true> : rs_bs_kernel<K, M, V, MODE, false>;
-      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsSmemBytes)) != cudaSuccess) return e;
-      kern<<<grid, kBsThreads, kBsSmemBytes, st>>>(p);
-    } else {
-      return cudaErrorInvalidValue;
-    }
-  } else {
-    if constexpr ((WHAT & 2) != 0) {
-      if (verify) {
-        if (packed) rs_bs_kernel<K, M, V, 0, true, true><<<grid, kBsThreads, 4096, st>>>(p);
-        else rs_bs_kernel<K, M, V, 0, false, true><<<grid, kBsThreads, 4096, st>>>(p);
-      } else if (packed) {
-        rs_bs_kernel<K, M, V, 0, true><<<grid, kBsThreads, 4096, st>>>(p);
-      } else {
-        rs_bs_kernel<K, M, V, 0, false><<<grid, kBsThreads, 4096, st>>>(p);
-      }
-    } else {
-      return cudaErrorInvalidValue;
-    }
+  if (crc && verify) return cudaErrorInvalidValue;
+  if (crc == 1) {
+    if constexpr ((WHAT & 1) != 0) return bs_launch_crc<K, M, V, 1>(p, grid, st);
+    return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
+  if (crc == 2) {
+    if constexpr ((WHAT & 4) != 0) return bs_launch_crc<K, M, V, 2>(p, grid, st);
+    return cudaErrorInvalidValue;
+  }
+  if constexpr ((WHAT & 2) != 0) {
+    if (verify) {
+      if (packed) rs_bs_kernel<K, M, V, 0, true, true><<<grid, kBsThreads, 4096, st>>>(p);
+      else rs_bs_kernel<K, M, V, 0, false, true><<<grid, kBsThreads, 4096, st>>>(p);
+    } else if (packed) {
+      rs_bs_kernel<K, M, V, 0, true><<<grid, kBsThreads, 4096, st>>>(p);
+    } else {
+      rs_bs_kernel<K, M, V, 0, false><<<grid, kBsThreads, 4096, st>>>(p);
+    }
+    return cudaGetLastError();
+  }
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace cbe

@@ -558,6 +558,76 @@ bool bs_layout_ok(const uint8_t* d_base, size_t shard_len, size_t shard_pitch, s
 
 
 
+bool bs_is_packed(size_t shard_len) {
+  const uint32_t pps = (uint32_t)((shard_len + kBsPiece - 1) / kBsPiece);
+  return pps < (uint32_t)kBsThreads && pps >= 8;
+}
+
+// Geometry of the bit-sliced kernels; shards shorter than a tile use packed mode (pieces of many
+// stripes share a tile).
+Geometry bs_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes) {
+  Geometry gm = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
+  if (bs_is_packed(shard_len)) {
+    const uint32_t pps = (uint32_t)((shard_len + kBsPiece - 1) / kBsPiece);
+    const uint64_t tiles = ((uint64_t)n_stripes * pps + kBsThreads - 1) / kBsThreads;
+    gm.n_seg = 2;               // a shard's pieces fall into at most two tiles
+    gm.packed_pps = pps;
+    gm.grid = (int)std::min<uint64_t>(tiles, (uint64_t)c.sm_count);
+  }
+  return gm;
+}
+
+// All bit-sliced passes of handle h over a device-resident batch whose stripes have n_slots shards.
+// in_slots (h->k entries, nullptr = 0..k-1) says which shard of the stripe each input is, outputs go to
+// out_first, out_first+1, ...  crc: 0 none, 1 every shard of this code, 2 only its outputs (the caller
+// finalises the partial remainders in d_part once all codes of the stripe have run).
+int bs_run(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t shard_len, size_t shard_pitch,
+           size_t stripe_pitch, size_t n_stripes, const Geometry& gm, int n_slots, const uint8_t* in_slots, int out_first,
+           int crc, uint32_t* d_part, int crc_poly, bool verify, int32_t* d_mismatch, bool ws = false) {
+  BsParams bp;
+  std::memset(&bp, 0, sizeof(bp));
+  bp.base = d_base;
+  bp.stripe_pitch = stripe_pitch;
+  bp.shard_pitch = shard_pitch;
+  bp.shard_len = (uint32_t)shard_len;
+  bp.n_stripes = (uint32_t)n_stripes;
+  bp.n_seg = gm.n_seg;
+  bp.tiles_per_seg = gm.tiles_per_seg;
+  bp.tiles_last = gm.tiles_last;
+  bp.n_slots = (uint32_t)n_slots;
+  bp.crc_part = crc ? d_part : nullptr;
+  bp.mismatch = verify ? d_mismatch : nullptr;
+  const int pi = crc_poly ? 1 : 0;
+  bp.slice_image = c.d_bs_slice[pi];
+  bp.fold_tables = ws ? c.d_bsw_fold[pi] : c.d_bs_fold[pi];
+  bp.kthread = ws ? c.d_bsw_kthread[pi] : c.d_bs_kthread[pi];
+  bp.poly = g.poly[pi].poly;
+  bp.k65536 = 65536u;
+  bp.packed_pps = gm.packed_pps;
+  if (h->k > (int)sizeof(bp.in_slot)) return CUBEEC_ERR_UNSUPPORTED;
+  for (int i = 0; i < h->k; i++) bp.in_slot[i] = in_slots ? in_slots[i] : (uint8_t)i;
+  if (ws) {
+    CU(launch_bsw(h->k, h->m, bp, gm.grid, stream));
+    g_launches++;
+    t_last_kernel = "rs_bsw_kernel";
+    return CUBEEC_OK;
+  }
+  // m > 4: one pass per group of parity rows (4 per pass with fused CRC, <= 6 without)
+  const int n_pass = crc ? h->bs_passes : h->bs_passes_plain;
+  for (int pass = 0; pass < n_pass; pass++) {
+    int r0 = 0, rows = h->m;
+    if (n_pass > 1 || h->m > 4) {
+      if (!bs_mp_pass_rows(h->k, h->m, crc ? 0 : 1, pass, &r0, &rows)) return CUBEEC_ERR_UNSUPPORTED;
+    }
+    for (int r = 0; r < rows && r < (int)sizeof(bp.out_slot); r++) bp.out_slot[r] = (uint8_t)(out_first + r0 + r);
+    const int mode = crc == 0 ? 0 : (crc == 1 && pass == 0 ? 1 : 2);
+    CU(launch_bs(h->k, h->m, pass, bp, mode, verify, gm.grid, stream));
+    g_launches++;
+  }
+  t_last_kernel = crc ? "rs_bs_kernel<crc>" : verify ? "rs_bs_kernel<verify>" : "rs_bs_kernel";
+  return CUBEEC_OK;
+}
+
 // Encode (mode 0) or verify (mode 1) a device-resident batch.  d_part: caller scratch of
 // crc_part_bytes() when CRCs are wanted, or nullptr to use the stream-ordered allocator.
 int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t shard_len,
@@ -569,60 +639,20 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
   const bool want_crc = mode == 0 && d_crc_out;
   if (h->bs_passes && g_force_kernel.load() != 1 && bs_layout_ok(d_base, shard_len, shard_pitch, stripe_pitch)) {
     // hot path: bit-sliced XOR-network kernel (bitslice.cu)
-    Geometry gm = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
-    // shards shorter than a tile: packed mode (pieces of many stripes share a tile)
-    const uint32_t pps = (uint32_t)((shard_len + kBsPiece - 1) / kBsPiece);
-    const bool packed = pps < (uint32_t)kBsThreads && pps >= 8;
-    // opt-in A/B aid: the warp-specialised fused kernel (bitslice_ws.cu; measured within +-3 % of
-    // rs_bs_kernel<crc>, see DESIGN.md "issue ceiling")
-    const bool ws = want_crc && !packed && g_force_kernel.load() == 5 && h->bs_passes == 1 && bsw_supported(h->k, h->m);
-    if (ws) gm = pick_geometry(c, shard_len, n_stripes, false, kBswTile);
-    if (packed) {
-      const uint64_t tiles = ((uint64_t)n_stripes * pps + kBsThreads - 1) / kBsThreads;
-      gm.n_seg = 2;               // a shard's pieces fall into at most two tiles
-      gm.packed_pps = pps;
-      gm.grid = (int)std::min<uint64_t>(tiles, (uint64_t)c.sm_count);
-    }
+    const bool ws = want_crc && g_force_kernel.load() == 5 && h->bs_passes == 1 && bsw_supported(h->k, h->m) &&
+                    !bs_is_packed(shard_len);
+    const Geometry gm = ws ? pick_geometry(c, shard_len, n_stripes, false, kBswTile) : bs_geometry(c, shard_len, n_stripes);
     bool own = false;
     if (want_crc && !d_part) {
       CU(cudaMallocAsync(&d_part, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
       own = true;
     }
-    if (want_crc && packed) CU(cudaMemsetAsync(d_part, 0, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
-    BsParams bp;
-    std::memset(&bp, 0, sizeof(bp));
-    bp.base = d_base;
-    bp.stripe_pitch = stripe_pitch;
-    bp.shard_pitch = shard_pitch;
-    bp.shard_len = (uint32_t)shard_len;
-    bp.n_stripes = (uint32_t)n_stripes;
-    bp.n_seg = gm.n_seg;
-    bp.tiles_per_seg = gm.tiles_per_seg;
-    bp.tiles_last = gm.tiles_last;
-    bp.n_slots = (uint32_t)n;
-    bp.crc_part = want_crc ? d_part : nullptr;
-    bp.mismatch = mode == 1 ? d_mismatch : nullptr;
-    const int pi = crc_poly ? 1 : 0;
-    bp.slice_image = c.d_bs_slice[pi];
-    bp.fold_tables = ws ? c.d_bsw_fold[pi] : c.d_bs_fold[pi];
-    bp.kthread = ws ? c.d_bsw_kthread[pi] : c.d_bs_kthread[pi];
-    bp.poly = g.poly[pi].poly;
-    bp.k65536 = 65536u;
-    bp.packed_pps = gm.packed_pps;
-    if (ws) {
-      CU(launch_bsw(h->k, h->m, bp, gm.grid, stream));
-      g_launches++;
-    } else {
-      // m > 4: one pass per group of 4 parity rows; the first also checksums the data shards
-      const int n_pass = want_crc ? h->bs_passes : h->bs_passes_plain;
-      for (int pass = 0; pass < n_pass; pass++) {
-        CU(launch_bs(h->k, h->m, pass, bp, want_crc ? (pass == 0 ? 1 : 2) : 0, mode == 1, gm.grid, stream));
-        g_launches++;
-      }
-    }
-    t_last_kernel = ws ? "rs_bsw_kernel" : want_crc ? "rs_bs_kernel<crc>" : mode == 1 ? "rs_bs_kernel<verify>" : "rs_bs_kernel";
+    if (want_crc && gm.packed_pps) CU(cudaMemsetAsync(d_part, 0, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
+    int rc = bs_run(h, c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, gm, n, nullptr, h->k,
+                    want_crc ? 1 : 0, want_crc ? d_part : nullptr, crc_poly, mode == 1, d_mismatch, ws);
+    if (rc) return rc;
     if (want_crc) {
-      int rc = finalize_crc(c, stream, d_part, n_stripes, n, shard_len, gm, crc_poly, nullptr, d_crc_out);
+      rc = finalize_crc(c, stream, d_part, n_stripes, n, shard_len, gm, crc_poly, nullptr, d_crc_out);
       if (rc) return rc;
       if (own) CU(cudaFreeAsync(d_part, stream));
     }
@@ -808,6 +838,96 @@ extern "C" int cubeec_dev_encode(cubeec_t* h, int device, void* d_base, size_t s
   }
   rc = dev_encode_impl(h, *c, lease.lane->stream, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch, n_stripes,
                        d_crc_out, crc_poly, 0, nullptr, d_part);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(lease.lane->stream));
+  return CUBEEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// LRC code modes (lrcEncoder.Encode, blobstore/common/ec/lrcencoder.go:35-80): global RS(N, M) over the
+// stripe, then per AZ a local RS((N+M)/AZ, L/AZ) over that AZ's data + global-parity shards
+// (codemode.GetECLayoutByAZ, codemode.go:301-318; e.g. EC6P10L2: AZ 0 = shards [0,1,2, 6..10] -> 16).
+// All passes run on the device-resident stripe: the data crosses PCIe once, every shard is
+// checksummed once (the local passes checksum only what they write).
+// ------------------------------------------------------------------------------------------
+namespace {
+struct LrcLayout {
+  int N, M, L, az, kl, ml;
+};
+
+int lrc_layout(const cubeec* hg, const cubeec* hl, int az, LrcLayout* y) {
+  if (!hg || !hl || az <= 0) return CUBEEC_ERR_INVALID_ARG;
+  y->N = hg->k;
+  y->M = hg->m;
+  y->az = az;
+  y->kl = hl->k;
+  y->ml = hl->m;
+  y->L = hl->m * az;
+  if (y->N % az || y->M % az || (y->N + y->M) / az != y->kl || y->ml <= 0) return CUBEEC_ERR_INVALID_ARG;
+  return CUBEEC_OK;
+}
+
+int dev_lrc_encode_impl(cubeec* hg, cubeec* hl, const LrcLayout& y, DevCtx& c, cudaStream_t stream, uint8_t* d_base,
+                        size_t shard_len, size_t shard_pitch, size_t stripe_pitch, size_t n_stripes,
+                        uint32_t* d_crc_out, int crc_poly, uint32_t* d_part) {
+  const int n_slots = y.N + y.M + y.L;
+  if (!hg->bs_passes || !hl->bs_passes || !bs_layout_ok(d_base, shard_len, shard_pitch, stripe_pitch)) {
+    t_last_error = "LRC device path needs the generated networks of both codes and a 32-byte aligned layout";
+    return CUBEEC_ERR_UNSUPPORTED;
+  }
+  const bool want_crc = d_crc_out != nullptr;
+  const Geometry gm = bs_geometry(c, shard_len, n_stripes);
+  bool own = false;
+  if (want_crc && !d_part) {
+    CU(cudaMallocAsync(&d_part, n_stripes * n_slots * gm.n_seg * sizeof(uint32_t), stream));
+    own = true;
+  }
+  if (want_crc && gm.packed_pps) CU(cudaMemsetAsync(d_part, 0, n_stripes * n_slots * gm.n_seg * sizeof(uint32_t), stream));
+  int rc = bs_run(hg, c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, gm, n_slots, nullptr, y.N,
+                  want_crc ? 1 : 0, d_part, crc_poly, false, nullptr);
+  if (rc) return rc;
+  for (int a = 0; a < y.az; a++) {
+    uint8_t in_slots[64];
+    int q = 0;
+    for (int i = 0; i < y.N / y.az; i++) in_slots[q++] = (uint8_t)(a * (y.N / y.az) + i);
+    for (int i = 0; i < y.M / y.az; i++) in_slots[q++] = (uint8_t)(y.N + a * (y.M / y.az) + i);
+    rc = bs_run(hl, c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, gm, n_slots, in_slots,
+                y.N + y.M + a * y.ml, want_crc ? 2 : 0, d_part, crc_poly, false, nullptr);
+    if (rc) return rc;
+  }
+  if (want_crc) {
+    rc = finalize_crc(c, stream, d_part, n_stripes, n_slots, shard_len, gm, crc_poly, nullptr, d_crc_out);
+    if (rc) return rc;
+    if (own) CU(cudaFreeAsync(d_part, stream));
+  }
+  return CUBEEC_OK;
+}
+}  // namespace
+
+extern "C" int cubeec_dev_lrc_encode(cubeec_t* global, cubeec_t* local, int az_count, int device, void* d_base,
+                                     size_t shard_len, size_t shard_pitch, size_t stripe_pitch, size_t n_stripes,
+                                     uint32_t* d_crc_out, int crc_poly, void* stream) {
+  LrcLayout y;
+  int rc = lrc_layout(global, local, az_count, &y);
+  if (rc) return rc;
+  if ((rc = ensure_init())) return rc;
+  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch))) return rc;
+  if (n_stripes == 0) return CUBEEC_OK;
+  DevCtx* c = ctx_for_device(device);
+  if (!c) return CUBEEC_ERR_INVALID_ARG;
+  CU(cudaSetDevice(device));
+  if (stream)
+    return dev_lrc_encode_impl(global, local, y, *c, (cudaStream_t)stream, (uint8_t*)d_base, shard_len, shard_pitch,
+                               stripe_pitch, n_stripes, d_crc_out, crc_poly, nullptr);
+  LaneLease lease;
+  if ((rc = lease.acquire(c))) return rc;
+  uint32_t* d_part = nullptr;
+  if (d_crc_out) {
+    if ((rc = lane_reserve(*lease.lane, 0, crc_part_bytes(*c, shard_len, n_stripes, y.N + y.M + y.L)))) return rc;
+    d_part = reinterpret_cast<uint32_t*>(lease.lane->d_aux);
+  }
+  rc = dev_lrc_encode_impl(global, local, y, *c, lease.lane->stream, (uint8_t*)d_base, shard_len, shard_pitch,
+                           stripe_pitch, n_stripes, d_crc_out, crc_poly, d_part);
   if (rc) return rc;
   CU(cudaStreamSynchronize(lease.lane->stream));
   return CUBEEC_OK;
@@ -1235,9 +1355,10 @@ extern "C" int cubeec_reconstruct_batch(cubeec_t* h, const cubeec_stripe_t* stri
 // and partitioned over the configured devices.
 // ------------------------------------------------------------------------------------------
 namespace {
+// hl != nullptr: LRC (h = global code, hl = local code, y = layout): stripes have N+M+L shards
 int encode_contig_device(cubeec* h, DevCtx* c, uint8_t* base, size_t S, size_t first, size_t count, size_t stripe_pitch,
-                         uint32_t* crc_out, int crc_poly) {
-  const int k = h->k, n = h->k + h->m, m = h->m;
+                         uint32_t* crc_out, int crc_poly, cubeec* hl = nullptr, const LrcLayout* y = nullptr) {
+  const int k = h->k, n = hl ? y->N + y->M + y->L : h->k + h->m, m = n - k;
   const size_t P = round_up(S, kAlign);
   const size_t dstripe = P * n;
   std::lock_guard<std::mutex> bulk(c->bulk_mu);
@@ -1269,7 +1390,8 @@ int encode_contig_device(cubeec* h, DevCtx* c, uint8_t* base, size_t S, size_t f
     uint32_t* d_part = crc_out ? reinterpret_cast<uint32_t*>(l.d_aux) : nullptr;
     uint32_t* d_crc = crc_out ? reinterpret_cast<uint32_t*>(l.d_aux + part_cap) : nullptr;
     if (crc_out && crc_part_bytes(*c, S, nb, n) > part_cap) return CUBEEC_ERR_UNSUPPORTED;
-    int rc = dev_encode_impl(h, *c, l.stream, l.d_buf, S, P, dstripe, nb, d_crc, crc_poly, 0, nullptr, d_part);
+    int rc = hl ? dev_lrc_encode_impl(h, hl, *y, *c, l.stream, l.d_buf, S, P, dstripe, nb, d_crc, crc_poly, d_part)
+                : dev_encode_impl(h, *c, l.stream, l.d_buf, S, P, dstripe, nb, d_crc, crc_poly, 0, nullptr, d_part);
     if (rc) return rc;
     if (crc_out)
       CU(cudaMemcpyAsync(crc_out + (first + done) * n, d_crc, nb * n * 4, cudaMemcpyDeviceToHost, l.stream));
@@ -1327,6 +1449,39 @@ extern "C" int cubeec_encode_contig(cubeec_t* h, uint8_t* base, size_t shard_len
         if (rc) return rc;
       }
   }
+  return CUBEEC_OK;
+}
+
+extern "C" int cubeec_lrc_encode_contig(cubeec_t* global, cubeec_t* local, int az_count, uint8_t* base, size_t shard_len,
+                                        size_t n_stripes, size_t stripe_pitch, uint32_t* crc_out, int crc_poly) {
+  LrcLayout y;
+  int rc = lrc_layout(global, local, az_count, &y);
+  if (rc) return rc;
+  if (!base || shard_len == 0) return CUBEEC_ERR_INVALID_ARG;
+  if (stripe_pitch < shard_len * (size_t)(y.N + y.M + y.L)) return CUBEEC_ERR_INVALID_ARG;
+  if ((rc = ensure_init())) return rc;
+  if (n_stripes == 0) return CUBEEC_OK;
+  const size_t n_ctx = g.ctx.size();
+  std::vector<int> rcs(n_ctx, CUBEEC_OK);
+  std::vector<std::string> errs(n_ctx);
+  auto work = [&](size_t ci) {
+    const size_t first = n_stripes * ci / n_ctx, last = n_stripes * (ci + 1) / n_ctx;
+    if (last > first) {
+      cudaSetDevice(g.ctx[ci]->device);
+      rcs[ci] = encode_contig_device(global, g.ctx[ci].get(), base, shard_len, first, last - first, stripe_pitch, crc_out,
+                                     crc_poly, local, &y);
+      if (rcs[ci]) errs[ci] = t_last_error;
+    }
+  };
+  if (n_ctx == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t ci = 0; ci < n_ctx; ci++) th.emplace_back(work, ci);
+    for (auto& t : th) t.join();
+  }
+  for (size_t ci = 0; ci < n_ctx; ci++)
+    if (rcs[ci]) { t_last_error = errs[ci]; return rcs[ci]; }
   return CUBEEC_OK;
 }
 

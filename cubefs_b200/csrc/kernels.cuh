@@ -138,6 +138,8 @@ struct BsParams {
   uint32_t n_slots;
   uint32_t* crc_part;                 // [n_stripes][n_slots][n_seg] or nullptr
   int32_t* mismatch;                  // verify variant: [n_stripes], set to 1 on any parity difference
+  uint8_t in_slot[24];                // shard of the stripe that is input c of the network (identity for a plain code)
+  uint8_t out_slot[8];                // shard that output r of this pass is written to
   const uint32_t* slice_image;        // global: 128 KiB replicated slicing tables (kBsSliceImageBytes)
   const uint32_t* fold_tables;        // global: [4][256] register * x^(8*(tile - piece))
   const uint32_t* kthread;            // global: [2][kBsThreads] x^(8*(tile - piece*(tid+1))), and the same times x^(8*tile)
@@ -183,6 +185,7 @@ struct BsRecParams {
 // network (the table kernels serve it).
 int bs_passes(int k, int m, const uint8_t* parity_rows, int plan);
 int bs_mp_passes(int k, int m, const uint8_t* parity_rows, int plan);           // bitslice_mp.cu
+bool bs_mp_pass_rows(int k, int m, int plan, int pass, int* r0, int* rows);     // m > 4 codes: rows of a pass
 bool bs_rec_supported(int k, int m);
 cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStream_t st);
 // crc: 0 none, 1 all shards (pass 0), 2 the pass's outputs only (pass > 0)

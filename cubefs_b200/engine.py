@@ -65,6 +65,9 @@ def load() -> C.CDLL:
     L.cubeec_encode_contig.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, C.c_size_t, C.c_int]
     L.cubeec_reconstruct_batch.argtypes = [vp, vp, C.c_size_t, C.c_int, vp]
     L.cubeec_dev_encode.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp, C.c_int, vp]
+    L.cubeec_lrc_encode_contig.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, C.c_int]
+    L.cubeec_dev_lrc_encode.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp,
+                                        C.c_int, vp]
     L.cubeec_dev_reconstruct.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp, C.c_int, vp]
     L.cubeec_dev_verify.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp]
     L.cubeec_crc32.argtypes = [vp, C.c_size_t, C.c_int, u32p]
@@ -107,6 +110,25 @@ def last_kernel() -> str:
 def force_kernel(which: int) -> None:
     """Measurement aid: 0 = automatic choice, 1 = generic table kernel only."""
     load().cubeec_debug_force_kernel(which)
+
+
+def lrc_encode_contig(global_eng: "RSEngine", local_eng: "RSEngine", az_count: int, buf: np.ndarray, shard_len: int,
+                      n_stripes: int, stripe_pitch: int, crc: bool = False, poly: int = 0, ptr: Optional[int] = None):
+    """cubeec_lrc_encode_contig: global RS(N,M) + per-AZ local RS in one device pass sequence (lrcencoder.go:35-80).
+    Returns the (n_stripes, N+M+L) checksums when crc is set."""
+    n = global_eng.k + global_eng.m + local_eng.m * az_count
+    crc_out = np.zeros((n_stripes, n), dtype=np.uint32) if crc else None
+    base = ptr if ptr is not None else buf.ctypes.data
+    _check(load().cubeec_lrc_encode_contig(global_eng._h, local_eng._h, az_count, base, shard_len, n_stripes, stripe_pitch,
+                                           crc_out.ctypes.data if crc else None, poly))
+    return crc_out
+
+
+def dev_lrc_encode(global_eng: "RSEngine", local_eng: "RSEngine", az_count: int, d_base: int, shard_len: int,
+                   shard_pitch: int, stripe_pitch: int, n_stripes: int, d_crc: int = 0, poly: int = 0, stream: int = 0,
+                   device: int = 0):
+    _check(load().cubeec_dev_lrc_encode(global_eng._h, local_eng._h, az_count, device, d_base, shard_len, shard_pitch,
+                                        stripe_pitch, n_stripes, d_crc or None, poly, stream or None))
 
 
 class StripeDesc(C.Structure):

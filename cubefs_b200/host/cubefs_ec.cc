@@ -148,6 +148,7 @@ class Engine {
   Engine(cubeec_t* h, int k, int m) : h_(h), k_(k), m_(m) {}
   ~Engine() { cubeec_destroy(h_); }
   int total() const { return k_ + m_; }
+  cubeec_t* handle() const { return h_; }
 
   static size_t shard_size(const Shards& s) {   // RS/reedsolomon.go:1332-1339
     for (const auto& x : s)
@@ -338,6 +339,20 @@ class LrcEncoder : public Encoder {
     const auto& t = cfg_.CodeMode;
     if ((int)shards.size() != t.N + t.M + t.L) return ErrInvalidShards;
     fillFullShards(shards, 0, shards.size());
+    // The PUT path hands over the shards of ONE ec.Buffer (buf.go:23-35): back to back, equal length.
+    // Then global + per-AZ local encodes are a single engine call that keeps the stripe in HBM
+    // (cubeec_lrc_encode_contig); otherwise compose the calls exactly as lrcencoder.go does.
+    if (!cfg_.EnableVerify) {
+      bool contig = true;
+      const size_t len = shards[0].len;
+      for (size_t i = 0; i < shards.size() && contig; i++)
+        contig = shards[i].len == len && shards[i].ptr == shards[0].ptr + i * len;
+      if (contig && len) {
+        int rc = cubeec_lrc_encode_contig(engine_->handle(), local_->handle(), t.AZCount, shards[0].ptr, len, 1,
+                                          len * shards.size(), nullptr, CUBEEC_CRC_IEEE);
+        if (rc != CUBEEC_ERR_UNSUPPORTED) return rc;
+      }
+    }
     Shards global(shards.begin(), shards.begin() + t.N + t.M);
     int rc = engine_->Encode(global);
     if (rc) return rc;

@@ -122,6 +122,21 @@ int cubeec_encode_contig(cubeec_t* h, uint8_t* base, size_t shard_len, size_t n_
                          size_t stripe_pitch, uint32_t* crc_out, uint32_t* blockcrc_out,
                          size_t block_payload, int crc_poly);
 
+/* LRC code modes in one call.  Replaces lrcEncoder.Encode (blobstore/common/ec/lrcencoder.go:35-80): the
+ * global reedsolomon.Encode over the first N+M shards followed by one localEngine.Encode per AZ over
+ * GetShardsInIdc (codemode.GetECLayoutByAZ, blobstore/common/codemode/codemode.go:301-318).
+ *   global = handle of RS(N, M); local = handle of RS((N+M)/az_count, L/az_count)  (both as NewEncoder
+ *   builds them, encoder.go:86,95)
+ *   layout = the LRC ec.Buffer: shard i (< N+M+L) of stripe s at base + s*stripe_pitch + i*shard_len;
+ *   data shards are read, the M global and L local parity shards are written.
+ *   crc_out: NULL or n_stripes*(N+M+L) checksums (stream_put.go:265-269 computes all of them).
+ * The stripe stays in HBM between the passes: N shards cross PCIe once, every shard is checksummed once.
+ * CUBEEC_ERR_UNSUPPORTED when one of the codes has no generated network (custom matrices): compose
+ * cubeec_encode calls as the reference does. */
+int cubeec_lrc_encode_contig(cubeec_t* global, cubeec_t* local, int az_count, uint8_t* base,
+                             size_t shard_len, size_t n_stripes, size_t stripe_pitch,
+                             uint32_t* crc_out, int crc_poly);
+
 /* One stripe of a batched reconstruct: the repair loop of
  * BS/blobnode/worker_slice_recover.go:822-885 (one entry per bid). */
 typedef struct cubeec_stripe {
@@ -146,6 +161,11 @@ int cubeec_reconstruct_batch(cubeec_t* h, const cubeec_stripe_t* stripes, size_t
 int cubeec_dev_encode(cubeec_t* h, int device, void* d_base, size_t shard_len, size_t shard_pitch,
                       size_t stripe_pitch, size_t n_stripes, uint32_t* d_crc_out, int crc_poly,
                       void* stream);
+/* Device-resident form of cubeec_lrc_encode_contig: stripes of N+M+L shards at shard_pitch (multiple of
+ * 32), d_crc_out = NULL or n_stripes*(N+M+L) device words. */
+int cubeec_dev_lrc_encode(cubeec_t* global, cubeec_t* local, int az_count, int device, void* d_base,
+                          size_t shard_len, size_t shard_pitch, size_t stripe_pitch, size_t n_stripes,
+                          uint32_t* d_crc_out, int crc_poly, void* stream);
 /* present: HOST array n_stripes*(k+m).  Regenerates every missing shard of every stripe in
  * one fused pass (missing parity is produced directly from the survivors). */
 int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, size_t shard_len, size_t shard_pitch,

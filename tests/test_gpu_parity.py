@@ -311,6 +311,58 @@ def test_linearity_and_roundtrip_at_scale(cb):
     assert torch.equal(c[:, :, :S], good[:, :, :S])
 
 
+def test_lrc_encode_fused(cb, oracle):
+    """cubeec_lrc_encode_contig / cubeec_dev_lrc_encode == lrcEncoder.Encode (lrcencoder.go:35-80): global
+    RS(N,M), then per AZ the local RS over [AZ data | AZ global parity] (codemode.GetECLayoutByAZ); parity
+    bytes and the CRC of every one of the N+M+L shards against the oracle.  All LRC code modes of
+    codemode.go (EC16P20L2, EC6P10L2, EC6P3L3, EC4P4L2, EC6P8L10) + a packed-size and a ragged-size case."""
+    import torch
+    modes = ((16, 20, 2, 2, 70001), (6, 10, 2, 2, 9000), (6, 3, 3, 3, 2048), (4, 4, 2, 2, 33000), (6, 8, 10, 2, 4097),
+             (6, 10, 2, 2, 349526 // 4))
+    for (N, M, L, az, S) in modes:
+        n, kl, ml = N + M + L, (N + M) // az, L // az
+        ns = 5
+        g_eng, l_eng = cb.RSEngine(N, M), cb.RSEngine(kl, ml)
+        g_ora, l_ora = oracle.RS(N, M), oracle.RS(kl, ml)
+        rng = np.random.default_rng(N * 100 + M)
+        # ---- host ec.Buffer layout (shards back to back, pitch = S) ----
+        host = rng.integers(0, 256, (ns, n, S), dtype=np.uint8)
+        want = host.copy()
+        for s in range(ns):
+            sh = [want[s, i].copy() for i in range(N + M)]
+            g_ora.encode(sh)
+            for i in range(N + M):
+                want[s, i] = sh[i]
+            for a in range(az):
+                idx = list(range(a * N // az, (a + 1) * N // az)) + list(range(N + a * M // az, N + (a + 1) * M // az))
+                loc = [want[s, i].copy() for i in idx] + [np.zeros(S, np.uint8) for _ in range(ml)]
+                l_ora.encode(loc)
+                for r in range(ml):
+                    want[s, N + M + a * ml + r] = loc[kl + r]
+        buf = host.copy()
+        buf[:, N:, :] = 0x5A   # parity areas hold garbage before the call
+        crc = cb.lrc_encode_contig(g_eng, l_eng, az, buf, S, ns, n * S, crc=True)
+        assert (buf == want).all(), (N, M, L, S)
+        for s in range(ns):
+            for i in range(n):
+                assert crc[s, i] == zlib.crc32(want[s, i].tobytes()), (N, M, L, S, s, i)
+        # ---- device-resident pitched layout, Castagnoli ----
+        P = (S + 127) // 128 * 128
+        dev = torch.zeros((ns, n, P), dtype=torch.uint8, device="cuda")
+        dev[:, :N, :S] = torch.from_numpy(host[:, :N, :]).cuda()
+        dcrc = torch.zeros(ns * n, dtype=torch.int32, device="cuda")
+        cb.dev_lrc_encode(g_eng, l_eng, az, dev.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr(), poly=1)
+        torch.cuda.synchronize()
+        assert (dev[:, :, :S].cpu().numpy() == want).all(), (N, M, L, S, "dev")
+        got = dcrc.cpu().numpy().view(np.uint32).reshape(ns, n)
+        for s in (0, ns - 1):
+            for i in range(n):
+                assert got[s, i] == oracle.crc32(want[s, i].tobytes(), 1), (N, M, L, S, s, i, "crc32c")
+    # layout errors: local code that does not match the AZ split
+    with pytest.raises(cb.CubeecError):
+        cb.lrc_encode_contig(cb.RSEngine(6, 10), cb.RSEngine(4, 1), 2, np.zeros(18 * 64, np.uint8), 64, 1, 18 * 64)
+
+
 def test_bitsliced_verify_kernel(cb):
     """rs_bs_kernel<verify> (reedSolomon.Verify, RS/reedsolomon.go:770-784): ok on encoded stripes;
     one flipped bit in any parity OR data shard -- first byte, last byte, middle -- fails exactly that

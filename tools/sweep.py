@@ -68,6 +68,33 @@ def main():
         cases = [(k, m, 1 << 20) for (k, m) in ((15, 12), (6, 6), (16, 20), (6, 10), (6, 3), (4, 4), (12, 4), (16, 4), (3, 3),
                                                  (10, 4), (12, 9), (24, 8), (6, 8))]
         forces = [0, 1]
+    if args.modes:
+        # LRC modes: global + per-AZ local passes fused on the device (cubeec_dev_lrc_encode)
+        for (N, M, L, az) in ((16, 20, 2, 2), (6, 10, 2, 2), (6, 3, 3, 3), (4, 4, 2, 2)):
+            S = 1 << 20
+            n, P = N + M + L, S
+            ns = max(1, int(args.gib * (1 << 30) // (n * P)))
+            ge, le = cb.RSEngine(N, M), cb.RSEngine((N + M) // az, L // az)
+            batch = torch.randint(0, 256, (ns, n, P), dtype=torch.uint8, device=dev)
+            dcrc = torch.zeros(ns * n, dtype=torch.int32, device=dev)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            for crc in ([0, 1] if args.crc else [0]):
+                f = lambda: cb.dev_lrc_encode(ge, le, az, batch.data_ptr(), S, P, n * P, ns,
+                                              d_crc=dcrc.data_ptr() if crc else 0, stream=st, device=dev.index)
+                for _ in range(3):
+                    f()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(dev)
+                e0.record()
+                for _ in range(5):
+                    f()
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / 5
+                moved = n * S * ns / (ms * 1e-3) / 1e9
+                print(json.dumps({"lrc": [N, M, L, az], "shard_bytes": S, "stripes": ns, "crc": bool(crc), "kernel": cb.last_kernel(),
+                                  "ms": round(ms, 4), "data_GiB_s": round(N * S * ns / (ms * 1e-3) / 2**30, 1),
+                                  "moved_GB_s": round(moved, 1), "frac_of_measured_hbm": round(moved / pk, 4)}), flush=True)
     engines = {}
     for (k, m, S), force in [(c, f) for c in cases for f in forces]:
         eng = engines.setdefault((k, m), cb.RSEngine(k, m))
