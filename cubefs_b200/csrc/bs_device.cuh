@@ -100,6 +100,27 @@ __device__ __forceinline__ uint32_t gf32_mul_dev(uint32_t a, uint32_t b, uint32_
   return r;
 }
 
+// u[q] = u[q] * kt for q in [Q0, Q1): the 32 successive x-multiples of the COMMON factor kt are computed
+// once and shared by all registers (3 + 3*(Q1-Q0) instructions per bit instead of 5*(Q1-Q0)).
+template <int Q0, int Q1, int N>
+__device__ __forceinline__ void gf32_mul_common(uint32_t (&u)[N], uint32_t kt, uint32_t poly) {
+  uint32_t r[N];
+#pragma unroll
+  for (int q = Q0; q < Q1; q++) r[q] = 0;
+  uint32_t a = kt;
+#pragma unroll 4
+  for (int i = 0; i < 32; i++) {
+#pragma unroll
+    for (int q = Q0; q < Q1; q++) {
+      r[q] ^= a & (uint32_t)((int32_t)u[q] >> 31);
+      u[q] <<= 1;
+    }
+    a = (a >> 1) ^ (poly & (0u - (a & 1u)));
+  }
+#pragma unroll
+  for (int q = Q0; q < Q1; q++) u[q] = r[q];
+}
+
 // compile-time dispatch on the shard index
 template <class Net, int C, int K>
 struct ApplyAt {

@@ -226,9 +226,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
         const uint32_t kt = active ? kth_s[pos + NT - PPS] : 0u;
         const uint32_t peers = __match_any_sync(0xffffffffu, stripe);
         const bool leader = active && (lane == __ffs(peers) - 1);
+        gf32_mul_common<C0, K + M>(crc_u, kt, p.poly);   // kt = 0 for inactive threads
 #pragma unroll
         for (int q = C0; q < K + M; q++) {
-          uint32_t u = active ? gf32_mul_dev(crc_u[q], kt, p.poly) : 0u;
+          uint32_t u = crc_u[q];
           crc_u[q] = 0;
           u = __reduce_xor_sync(peers, u);
           if (leader) atomicXor(&red2_s[(stripe - stripe0) * (K + M) + q], u);
@@ -291,9 +292,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
     }
     if (CRC && p.crc_part) {
       const uint32_t kt = kth_s[skipped_tile ? NT + tid : tid];
+      gf32_mul_common<C0, K + M>(crc_u, kt, p.poly);
 #pragma unroll
       for (int q = C0; q < K + M; q++) {
-        uint32_t u = gf32_mul_dev(crc_u[q], kt, p.poly);
+        uint32_t u = crc_u[q];
         crc_u[q] = 0;
         u = __reduce_xor_sync(0xffffffffu, u);
         if (lane == 0) red_s[q * NW + warp] = u;

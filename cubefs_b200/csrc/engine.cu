@@ -1355,9 +1355,15 @@ extern "C" int cubeec_reconstruct_batch(cubeec_t* h, const cubeec_stripe_t* stri
 // and partitioned over the configured devices.
 // ------------------------------------------------------------------------------------------
 namespace {
-// hl != nullptr: LRC (h = global code, hl = local code, y = layout): stripes have N+M+L shards
+int dev_crc32_impl(DevCtx& c, cudaStream_t st, const uint8_t* d_base, size_t len, size_t pitch, size_t n_buffers,
+                   size_t block, int crc_poly, uint32_t* d_whole, uint32_t* d_blocks);
+
+// hl != nullptr: LRC (h = global code, hl = local code, y = layout): stripes have N+M+L shards.
+// blockcrc_out: per-block CRCs (crc32block payloads of block_payload bytes) of every shard, computed on the
+// device-resident stripes before they are copied back (one more HBM pass, no extra PCIe traffic).
 int encode_contig_device(cubeec* h, DevCtx* c, uint8_t* base, size_t S, size_t first, size_t count, size_t stripe_pitch,
-                         uint32_t* crc_out, int crc_poly, cubeec* hl = nullptr, const LrcLayout* y = nullptr) {
+                         uint32_t* crc_out, int crc_poly, cubeec* hl = nullptr, const LrcLayout* y = nullptr,
+                         uint32_t* blockcrc_out = nullptr, size_t block_payload = 0) {
   const int k = h->k, n = hl ? y->N + y->M + y->L : h->k + h->m, m = n - k;
   const size_t P = round_up(S, kAlign);
   const size_t dstripe = P * n;
@@ -1370,12 +1376,14 @@ int encode_contig_device(cubeec* h, DevCtx* c, uint8_t* base, size_t S, size_t f
   // CRC scratch bound for any chunk of <= `chunk` stripes: nb * n_seg(nb) <= 8*SMs + nb
   const size_t part_cap = round_up((size_t)n * (8 * (size_t)c->sm_count + chunk + 8) * 4, 256);
   const size_t crc_cap = round_up(chunk * n * 4, 256);
+  const size_t units = blockcrc_out ? (S + block_payload - 1) / block_payload : 0;
+  const size_t blk_cap = round_up(chunk * n * units * 4, 256);
   std::vector<std::unique_ptr<LaneLease>> leases;
   for (int q = 0; q < n_lanes; q++) {
     auto ls = std::make_unique<LaneLease>();
     int rc = ls->acquire(c);
     if (rc) return rc;
-    rc = lane_reserve(*ls->lane, dstripe * chunk, crc_out ? part_cap + crc_cap : 256);
+    rc = lane_reserve(*ls->lane, dstripe * chunk, (crc_out ? part_cap + crc_cap : 256) + blk_cap);
     if (rc) return rc;
     leases.push_back(std::move(ls));
   }
@@ -1395,6 +1403,14 @@ int encode_contig_device(cubeec* h, DevCtx* c, uint8_t* base, size_t S, size_t f
     if (rc) return rc;
     if (crc_out)
       CU(cudaMemcpyAsync(crc_out + (first + done) * n, d_crc, nb * n * 4, cudaMemcpyDeviceToHost, l.stream));
+    if (blockcrc_out) {
+      // shard i of stripe s is buffer s*n + i of the lane (pitch P): same order as blockcrc_out
+      uint32_t* d_blk = reinterpret_cast<uint32_t*>(l.d_aux + (crc_out ? part_cap + crc_cap : 256));
+      rc = dev_crc32_impl(*c, l.stream, l.d_buf, S, P, nb * (size_t)n, block_payload, crc_poly, nullptr, d_blk);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(blockcrc_out + (first + done) * n * units, d_blk, nb * n * units * 4, cudaMemcpyDeviceToHost,
+                         l.stream));
+    }
     for (size_t s = 0; s < nb && m > 0; s++) {
       uint8_t* dst = base + (first + done + s) * stripe_pitch + (size_t)k * S;
       CU(cudaMemcpy2DAsync(dst, S, l.d_buf + s * dstripe + (size_t)k * P, P, S, (size_t)m, cudaMemcpyDeviceToHost,
@@ -1417,6 +1433,7 @@ extern "C" int cubeec_encode_contig(cubeec_t* h, uint8_t* base, size_t shard_len
   if (rc) return rc;
   if (n_stripes == 0) return CUBEEC_OK;
   if (h->m == 0 && !crc_out && !blockcrc_out) return CUBEEC_OK;
+  if (blockcrc_out && block_payload > 0xFFFFFFF0ull) return CUBEEC_ERR_INVALID_ARG;
   const size_t n_ctx = g.ctx.size();
   std::vector<int> rcs(n_ctx, CUBEEC_OK);
   std::vector<std::string> errs(n_ctx);
@@ -1425,7 +1442,7 @@ extern "C" int cubeec_encode_contig(cubeec_t* h, uint8_t* base, size_t shard_len
     if (last > first) {
       cudaSetDevice(g.ctx[ci]->device);
       rcs[ci] = encode_contig_device(h, g.ctx[ci].get(), base, shard_len, first, last - first, stripe_pitch, crc_out,
-                                     crc_poly);
+                                     crc_poly, nullptr, nullptr, blockcrc_out, block_payload);
       if (rcs[ci]) errs[ci] = t_last_error;
     }
   };
@@ -1438,17 +1455,6 @@ extern "C" int cubeec_encode_contig(cubeec_t* h, uint8_t* base, size_t shard_len
   }
   for (size_t ci = 0; ci < n_ctx; ci++)
     if (rcs[ci]) { t_last_error = errs[ci]; return rcs[ci]; }
-  if (blockcrc_out) {
-    // per-block CRCs of every shard (crc32block framing order): one flat pass per stripe row set
-    const int n = h->k + h->m;
-    const size_t units = (shard_len + block_payload - 1) / block_payload;
-    for (size_t s = 0; s < n_stripes; s++)
-      for (int i = 0; i < n; i++) {
-        rc = cubeec_crc32_blocks(base + s * stripe_pitch + (size_t)i * shard_len, shard_len, block_payload, crc_poly,
-                                 blockcrc_out + (s * n + i) * units, nullptr);
-        if (rc) return rc;
-      }
-  }
   return CUBEEC_OK;
 }
 

@@ -206,6 +206,23 @@ def test_encode_contig_batch(cb, oracle):
             assert (buf[s, i * S:(i + 1) * S] == sh[i]).all(), (s, i)
             assert crc[s, i] == zlib.crc32(sh[i].tobytes())
             assert blk[s, i, 0] == zlib.crc32(sh[i].tobytes())
+    # shards spanning several crc32block payloads (65,532 B; the last block is short): per-block CRCs come
+    # from the device-resident stripes, in blobnode framing order (crc32block/block.go:38-49)
+    k, m, S, ns = 6, 3, 65532 * 2 + 4711, 5
+    buf = rng.integers(0, 256, (ns, (k + m) * S), dtype=np.uint8)
+    ref = buf.copy()
+    eng = cb.RSEngine(k, m)
+    crc, blk = eng.encode_contig(buf, S, ns, (k + m) * S, crc=True, block_payload=65532)
+    ora = oracle.RS(k, m)
+    assert blk.shape == (ns, k + m, 3)
+    for s in range(ns):
+        sh = [ref[s, i * S:(i + 1) * S].copy() for i in range(k + m)]
+        ora.encode(sh)
+        for i in range(k + m):
+            raw = sh[i].tobytes()
+            assert (buf[s, i * S:(i + 1) * S] == sh[i]).all(), (s, i)
+            assert crc[s, i] == zlib.crc32(raw)
+            assert [int(x) for x in blk[s, i]] == [zlib.crc32(raw[o:o + 65532]) for o in range(0, S, 65532)], (s, i)
 
 
 def test_reconstruct_batch_with_verify(cb, oracle):
