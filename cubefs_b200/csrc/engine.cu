@@ -603,7 +603,6 @@ int bs_run(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t sh
   bp.fold_tables = ws ? c.d_bsw_fold[pi] : c.d_bs_fold[pi];
   bp.kthread = ws ? c.d_bsw_kthread[pi] : c.d_bs_kthread[pi];
   bp.poly = g.poly[pi].poly;
-  bp.k65536 = 65536u;
   bp.packed_pps = gm.packed_pps;
   if (h->k > (int)sizeof(bp.in_slot)) return CUBEEC_ERR_UNSUPPORTED;
   for (int i = 0; i < h->k; i++) bp.in_slot[i] = in_slots ? in_slots[i] : (uint8_t)i;

@@ -144,7 +144,6 @@ struct BsParams {
   const uint32_t* fold_tables;        // global: [4][256] register * x^(8*(tile - piece))
   const uint32_t* kthread;            // global: [2][kBsThreads] x^(8*(tile - piece*(tid+1))), and the same times x^(8*tile)
   uint32_t poly;
-  uint32_t k65536;                    // = 65536, opaque to the compiler (see slice4 in bitslice.cu)
   uint32_t packed_pps;                // 0 = one shard spans >= 1 tile; else 64-byte pieces per shard (< kBsThreads): packed mode
 };
 
