@@ -12,38 +12,13 @@ namespace cbe {
 
 using namespace bsdev;
 
-#ifdef CUBEEC_BS_CRC_CALL
-// Experiment: the slicing-by-4 absorption of one 32-byte column as a real function (one copy of its 80
-// instructions instead of one per shard) to shrink the hot loop below the 32 KB instruction cache.
-__device__ __noinline__ uint32_t crc_absorb8(uint32_t u, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
-                                             uint32_t w5, uint32_t w6, uint32_t w7, uint32_t lane_base) {
-  const uint32_t w[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const uint32_t y = u ^ w[i];
-    const uint32_t a0 = byte_madd<0>(y, 256u, 256u << 16, lane_base);
-    const uint32_t a1 = byte_madd<1>(y, 256u, 256u << 16, lane_base);
-    const uint32_t a2 = byte_madd<2>(y, 256u, 256u << 16, lane_base);
-    const uint32_t a3 = byte_madd<3>(y, 256u, 256u << 16, lane_base);
-    u = lds32_off<65536 + 128>(a0) ^ lds32_off<65536>(a1) ^ lds32_off<128>(a2) ^ lds32_off<0>(a3);
-  }
-  return u;
-}
-#endif
-
-// Stripe slot of local shard q (inputs 0..K-1, outputs K..K+M-1).  A run-time index into the kernel
-// parameter arrays would make the compiler copy the whole parameter block to local memory (measured:
-// fused kernel 52 % -> 42 %); a compare chain on constant indices keeps them in the constant bank.
-template <int K, int M>
-__device__ __forceinline__ uint32_t bs_slot(const BsParams& p, uint32_t q) {
-  uint32_t r = 0;
-#pragma unroll
-  for (int i = 0; i < K; i++)
-    if (q == (uint32_t)i) r = p.in_slot[i];
-#pragma unroll
-  for (int i = 0; i < M; i++)
-    if (q == (uint32_t)(K + i)) r = p.out_slot[i];
-  return r;
+// Stripe slot of the CRC register with local index q (inputs 0..K-1, outputs K..K+M-1).  The data shards
+// are checksummed (CRC mode 1) only by a code whose inputs are slots 0..K-1 -- LRC local stripes use
+// mode 2 -- and the outputs of a pass are consecutive slots, so no table lookup is needed.  (A run-time
+// index into the parameter arrays made the compiler copy the parameter block to local memory: the fused
+// kernel fell from 52 % to 42 %.)
+__device__ __forceinline__ uint32_t bs_slot(const BsParams& p, uint32_t q, uint32_t k) {
+  return q < k ? q : (uint32_t)p.out_slot[0] + (q - k);
 }
 
 // VERIFY (reedSolomon.Verify / checkSomeShards, RS/reedsolomon.go:770-784,1287-1301): the computed
@@ -175,14 +150,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
         for (int i = 0; i < 8; i++) w[i] &= msk[i];
       }
       if (CRC == 1) {
-#ifdef CUBEEC_BS_CRC_CALL
-        crc_u[c] = crc_absorb8(crc_u[c], w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], lane_base);
-#else
         uint32_t u = crc_u[c];
 #pragma unroll
         for (int i = 0; i < 8; i++) u = slice4(u ^ w[i]);
         crc_u[c] = u;
-#endif
       }
       bit_transpose8(w);
       ApplyAt<Net, 0, K>::run(c, w, acc);   // c is a compile-time constant after unrolling
@@ -212,14 +183,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
         stg256(sbase + (size_t)p.out_slot[r] * p.shard_pitch + col, o);
       }
       if (CRC) {
-#ifdef CUBEEC_BS_CRC_CALL
-        crc_u[K + r] = crc_absorb8(crc_u[K + r], o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], lane_base);
-#else
         uint32_t u = crc_u[K + r];
 #pragma unroll
         for (int i = 0; i < 8; i++) u = slice4(u ^ o[i]);
         crc_u[K + r] = u;
-#endif
       }
     }
   };
@@ -280,7 +247,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
         for (uint32_t i = tid; i < nstr * (K + M); i += NT) {
           const uint32_t sj = stripe0 + i / (K + M), q = i % (K + M);
           const uint32_t segidx = tile - (uint32_t)(((uint64_t)sj * PPS) / NT);   // 0 or 1: a shard spans at most two tiles
-          if (q >= (uint32_t)C0) p.crc_part[((size_t)sj * p.n_slots + bs_slot<K, M>(p, q)) * 2 + segidx] = red2_s[i];
+          if (q >= (uint32_t)C0) p.crc_part[((size_t)sj * p.n_slots + bs_slot(p, q, (uint32_t)K)) * 2 + segidx] = red2_s[i];
         }
         __syncthreads();
       }
@@ -347,7 +314,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
         uint32_t u = 0;
 #pragma unroll
         for (int w2 = 0; w2 < NW; w2++) u ^= red_s[tid * NW + w2];
-        p.crc_part[((size_t)s * p.n_slots + bs_slot<K, M>(p, (uint32_t)tid)) * p.n_seg + seg] = u;
+        p.crc_part[((size_t)s * p.n_slots + bs_slot(p, (uint32_t)tid, (uint32_t)K)) * p.n_seg + seg] = u;
       }
       __syncthreads();
     }

@@ -605,6 +605,7 @@ int bs_run(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t sh
   bp.poly = g.poly[pi].poly;
   bp.packed_pps = gm.packed_pps;
   if (h->k > (int)sizeof(bp.in_slot)) return CUBEEC_ERR_UNSUPPORTED;
+  if (crc == 1 && in_slots) return CUBEEC_ERR_INVALID_ARG;   // data CRCs only with the identity input map (bs_slot)
   for (int i = 0; i < h->k; i++) bp.in_slot[i] = in_slots ? in_slots[i] : (uint8_t)i;
   if (ws) {
     CU(launch_bsw(h->k, h->m, bp, gm.grid, stream));

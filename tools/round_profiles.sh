@@ -1,5 +1,6 @@
 set -x
 mkdir -p gpurun_out/p
+timeout 300 python -m pytest tests -x -q -m gpu > gpurun_out/p/pytest_gpu.log 2>&1; tail -2 gpurun_out/p/pytest_gpu.log
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/p/launches_encode_crc.csv python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/p/launches_run.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rs_bs_kernel -s 3 -c 1 -o /tmp/bs_crc python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/p/bs_crc.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rs_bs_kernel -s 3 -c 1 -o /tmp/bs_nocrc python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --crc 0 > gpurun_out/p/bs_nocrc.log 2>&1
