@@ -1,4 +1,5 @@
-// bitslice.cu -- the bit-sliced RS encode kernel with fused CRC32 (sm_100a).
+// bitslice.cu -- the bit-sliced RS encode kernel with fused CRC32 (sm_100a): design notes, the syndrome
+// reconstruct kernel and the single-pass instantiations.  The kernel template itself is bs_kernel.cuh.
 //
 // The hot kernel of BASELINE config C2 (RS(12,4) encode + CRC32 of all shards in one HBM pass).
 // Replaces reedSolomon.Encode's SIMD loop (RS/reedsolomon.go:609-625,897-1134; kernels
@@ -11,7 +12,7 @@
 // transpose (12 delta swaps), and multiplication by the (compile-time) matrix coefficients becomes
 // a fixed XOR network on planes: 3-input XORs = one LOP3 each, no memory traffic.  The CRC runs
 // on the same registers before the transpose: slicing-by-4 over the 8 words with lane-private
-// (conflict-free) copies of the tables in shared memory, one PRMT to form each lookup address.
+// (conflict-free) copies of the tables in shared memory, one IDP.2A (FMA pipe) to form each lookup address.
 // Per thread the CRC registers advance Horner-style over the tiles; partial remainders are
 // aligned and XOR-reduced once per work item and finished by crc_finalize_kernel.
 #include "bs_kernel.cuh"
