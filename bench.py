@@ -245,7 +245,7 @@ def main():
     ap.add_argument("--cpu-stripes", type=int, default=256, help="stripes in the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "table", "ws", "bsrec"],
+    ap.add_argument("--kernel", default="auto", choices=["auto", "table", "ws", "bsrec", "rolled"],
                     help="A/B aid: table = generic table kernel, ws = warp-specialised fused encode+CRC kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -276,6 +276,8 @@ def main():
         cb.force_kernel(5)
     if args.kernel == "bsrec":
         cb.force_kernel(2)
+    if args.kernel == "rolled":
+        cb.force_kernel(6)
 
     # coding matrix: built on rank 0, NCCL-broadcast to the other ranks (the only shared state)
     if rank == 0:

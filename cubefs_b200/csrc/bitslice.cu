@@ -248,6 +248,30 @@ cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStre
   return cudaErrorInvalidValue;
 }
 
+// experiment: rolled fused kernel (see bs_kernel.cuh), non-packed, CRC of every shard
+#define CUBEEC_BS_ROLLED_CONFIGS(X) X(12, 4) X(6, 2) X(10, 4)
+bool bs_rolled_supported(int k, int m) {
+#define X(KK, MM) \
+  if (k == KK && m == MM) return true;
+  CUBEEC_BS_ROLLED_CONFIGS(X)
+#undef X
+  return false;
+}
+cudaError_t launch_bs_rolled(int k, int m, const BsParams& p, int grid, cudaStream_t st) {
+  if (p.packed_pps) return cudaErrorInvalidValue;
+#define X(KK, MM)                                                                                             \
+  if (k == KK && m == MM) {                                                                                   \
+    auto kern = rs_bs_kernel<KK, MM, 0, 1, false, false, true>;                                               \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsSmemBytes); \
+    if (e != cudaSuccess) return e;                                                                           \
+    kern<<<grid, kBsThreads, kBsSmemBytes, st>>>(p);                                                          \
+    return cudaGetLastError();                                                                                \
+  }
+  CUBEEC_BS_ROLLED_CONFIGS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_bs(int k, int m, int pass, const BsParams& p, int crc, bool verify, int grid, cudaStream_t st) {
   // single-pass codes serve every variant; the m > 4 codes have a pass plan per variant (bitslice_mp.cu)
   // outputs-only CRC (4) exists for the LRC local-stripe codes

@@ -134,6 +134,25 @@ struct ApplyAt<Net, K, K> {
   static __device__ __forceinline__ void run(int, const uint32_t (&)[8], uint32_t (&)[8 * Net::M]) {}
 };
 
+// run-time dispatch on the shard index (rolled variant): apply network C, park the CRC register of shard C
+// and pick up the one of shard C+1.  Only indices of the parity of C0 are compared (step 2).
+template <class Net, int C, int K>
+struct RollAt {
+  template <int NQ>
+  static __device__ __forceinline__ void run(int c, const uint32_t (&w)[8], uint32_t (&acc)[8 * Net::M], uint32_t (&crc_u)[NQ],
+                                             uint32_t& u) {
+    if constexpr (C < K) {
+      if (c == C) {
+        Net::template apply<C>(w, acc);
+        crc_u[C] = u;
+        u = crc_u[C + 1];
+      } else {
+        RollAt<Net, C + 2, K>::run(c, w, acc, crc_u, u);
+      }
+    }
+  }
+};
+
 
 }  // namespace bsdev
 }  // namespace cbe

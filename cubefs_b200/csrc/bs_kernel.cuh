@@ -29,7 +29,13 @@ __device__ __forceinline__ uint32_t bs_slot(const BsParams& p, uint32_t q, uint3
 // 0 = RS(K, M), else rows [kRow0, kRow0+M) of RS(K, kTotalM).  Which shard of the stripe input c / output
 // r is comes from p.in_slot / p.out_slot (identity + kRow0 for a plain code; the AZ's shard list for an
 // LRC local stripe, codemode.GetECLayoutByAZ).
-template <int K, int M, int V, int CRC, bool PACKED, bool VERIFY = false>
+//
+// ROLLED (experiment, cubeec_debug_force_kernel(6)): the fully unrolled column loop of the fused-CRC
+// variant is 48 KB of straight-line code, more than the 32 KB instruction cache, and anything that lets
+// warps drift apart in it costs throughput.  ROLLED keeps ONE copy of the CRC absorption
+// and the bit transpose in a loop over shard pairs and dispatches only the per-shard XOR network through
+// a switch: about 23 KB of hot code, no calls.
+template <int K, int M, int V, int CRC, bool PACKED, bool VERIFY = false, bool ROLLED = false>
 __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) {
   static_assert(!(CRC && VERIFY), "verify does not checksum");
   using Net = BsNet<K, M, V>;
@@ -158,13 +164,36 @@ __global__ void __launch_bounds__(kBsThreads, 1) rs_bs_kernel(const BsParams p) 
       bit_transpose8(w);
       ApplyAt<Net, 0, K>::run(c, w, acc);   // c is a compile-time constant after unrolling
     };
+    if constexpr (ROLLED && FULL && CRC == 1) {
+      static_assert(!ROLLED || (K % 2 == 0 && !VERIFY), "rolled variant: even k, encode only");
+      // two shard buffers alternate; the running CRC register u is swapped with crc_u[] inside the
+      // switch cases, where the shard index is a constant (inputs are slots 0..K-1 in CRC mode 1)
+      uint32_t (&a)[8] = ring[0];
+      uint32_t (&b)[8] = ring[1];
+      ldg256(src, a);
+      uint32_t u = crc_u[0];
+#pragma unroll 1
+      for (int c = 0; c < K; c += 2) {
+        ldg256(src + (size_t)(c + 1) * p.shard_pitch, b);
 #pragma unroll
-    for (int c = 0; c < DEPTH && c < K; c++)
-      if (live) ldg256(src + (size_t)p.in_slot[c] * p.shard_pitch, ring[c % (DEPTH + 1)]);
+        for (int i = 0; i < 8; i++) u = slice4(u ^ a[i]);
+        bit_transpose8(a);
+        RollAt<Net, 0, K>::run(c, a, acc, crc_u, u);
+        if (c + 2 < K) ldg256(src + (size_t)(c + 2) * p.shard_pitch, a);
 #pragma unroll
-    for (int c = 0; c < K; c++) {
-      if (c + DEPTH < K && live) ldg256(src + (size_t)p.in_slot[c + DEPTH] * p.shard_pitch, ring[(c + DEPTH) % (DEPTH + 1)]);
-      shard(c, ring[c % (DEPTH + 1)]);
+        for (int i = 0; i < 8; i++) u = slice4(u ^ b[i]);
+        bit_transpose8(b);
+        RollAt<Net, 1, K>::run(c + 1, b, acc, crc_u, u);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < DEPTH && c < K; c++)
+        if (live) ldg256(src + (size_t)p.in_slot[c] * p.shard_pitch, ring[c % (DEPTH + 1)]);
+#pragma unroll
+      for (int c = 0; c < K; c++) {
+        if (c + DEPTH < K && live) ldg256(src + (size_t)p.in_slot[c + DEPTH] * p.shard_pitch, ring[(c + DEPTH) % (DEPTH + 1)]);
+        shard(c, ring[c % (DEPTH + 1)]);
+      }
     }
 #pragma unroll
     for (int r = 0; r < M; r++) {

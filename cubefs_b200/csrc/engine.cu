@@ -584,7 +584,7 @@ Geometry bs_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes) {
 // finalises the partial remainders in d_part once all codes of the stripe have run).
 int bs_run(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t shard_len, size_t shard_pitch,
            size_t stripe_pitch, size_t n_stripes, const Geometry& gm, int n_slots, const uint8_t* in_slots, int out_first,
-           int crc, uint32_t* d_part, int crc_poly, bool verify, int32_t* d_mismatch, bool ws = false) {
+           int crc, uint32_t* d_part, int crc_poly, bool verify, int32_t* d_mismatch, bool ws = false, bool rolled = false) {
   BsParams bp;
   std::memset(&bp, 0, sizeof(bp));
   bp.base = d_base;
@@ -611,6 +611,13 @@ int bs_run(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t sh
     CU(launch_bsw(h->k, h->m, bp, gm.grid, stream));
     g_launches++;
     t_last_kernel = "rs_bsw_kernel";
+    return CUBEEC_OK;
+  }
+  if (rolled) {
+    for (int r = 0; r < h->m; r++) bp.out_slot[r] = (uint8_t)(out_first + r);
+    CU(launch_bs_rolled(h->k, h->m, bp, gm.grid, stream));
+    g_launches++;
+    t_last_kernel = "rs_bs_kernel<crc,rolled>";
     return CUBEEC_OK;
   }
   // m > 4: one pass per group of parity rows (4 per pass with fused CRC, <= 6 without)
@@ -649,8 +656,9 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
       own = true;
     }
     if (want_crc && gm.packed_pps) CU(cudaMemsetAsync(d_part, 0, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
+    const bool rolled = want_crc && g_force_kernel.load() == 6 && !gm.packed_pps && bs_rolled_supported(h->k, h->m);
     int rc = bs_run(h, c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, gm, n, nullptr, h->k,
-                    want_crc ? 1 : 0, want_crc ? d_part : nullptr, crc_poly, mode == 1, d_mismatch, ws);
+                    want_crc ? 1 : 0, want_crc ? d_part : nullptr, crc_poly, mode == 1, d_mismatch, ws, rolled);
     if (rc) return rc;
     if (want_crc) {
       rc = finalize_crc(c, stream, d_part, n_stripes, n, shard_len, gm, crc_poly, nullptr, d_crc_out);

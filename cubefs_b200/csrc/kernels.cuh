@@ -190,6 +190,8 @@ cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStre
 // crc: 0 none, 1 all shards (pass 0), 2 the pass's outputs only (pass > 0)
 cudaError_t launch_bs(int k, int m, int pass, const BsParams& p, int crc, bool verify, int grid, cudaStream_t st);
 cudaError_t launch_bs_mp(int k, int m, int pass, const BsParams& p, int crc, bool verify, int grid, cudaStream_t st);
+bool bs_rolled_supported(int k, int m);                                        // experiment: rolled fused kernel
+cudaError_t launch_bs_rolled(int k, int m, const BsParams& p, int grid, cudaStream_t st);
 bool bsw_supported(int k, int m);                              // bitslice_ws.cu has this configuration (and its register split is safe)
 cudaError_t launch_bsw(int k, int m, const BsParams& p, int grid, cudaStream_t st);
 

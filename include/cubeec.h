@@ -197,7 +197,8 @@ uint64_t cubeec_kernel_launches(void);
 const char* cubeec_last_kernel(void);
 /* Measurement aid: 0 = automatic kernel choice (default), 1 = no bit-sliced kernels, 2 = bit-sliced
  * syndrome kernel for cubeec_dev_reconstruct, 3 = generic (runtime-arity) table kernel only,
- * 5 = warp-specialised fused encode+CRC kernel (rs_bsw_kernel, RS(12,4) only) instead of rs_bs_kernel<crc>. */
+ * 5 = warp-specialised fused encode+CRC kernel (rs_bsw_kernel, RS(12,4) only) instead of rs_bs_kernel<crc>,
+ * 6 = rolled-loop fused encode+CRC kernel (smaller hot loop; RS(12,4), (10,4), (6,2)). */
 void cubeec_debug_force_kernel(int which);
 
 #ifdef __cplusplus

@@ -380,6 +380,37 @@ def test_lrc_encode_fused(cb, oracle):
         cb.lrc_encode_contig(cb.RSEngine(6, 10), cb.RSEngine(4, 1), 2, np.zeros(18 * 64, np.uint8), 64, 1, 18 * 64)
 
 
+def test_rolled_fused_kernel(cb, oracle):
+    """Opt-in rolled-loop variant of the fused encode+CRC kernel (cubeec_debug_force_kernel(6)): same parity
+    bytes and CRCs (both polynomials) as the oracle on whole-stripe, segmented and ragged geometries."""
+    import torch
+    for (k, m) in ((12, 4), (10, 4), (6, 2)):
+        n = k + m
+        eng = cb.RSEngine(k, m)
+        ora = oracle.RS(k, m)
+        for (S, ns, poly) in ((349526, 3, 0), (32768 * 2, 2, 1), (32768 * 3 + 1, 2, 0), (100001, 700, 1)):
+            P = (S + 127) // 128 * 128
+            rng = np.random.default_rng(S + k)
+            host = rng.integers(0, 256, (ns, n, P), dtype=np.uint8)
+            cb.force_kernel(6)
+            try:
+                dev = torch.from_numpy(host).cuda()
+                dcrc = torch.zeros(ns * n, dtype=torch.int32, device="cuda")
+                eng.dev_encode(dev.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr(), poly=poly)
+                assert cb.last_kernel() == "rs_bs_kernel<crc,rolled>"
+                torch.cuda.synchronize()
+            finally:
+                cb.force_kernel(0)
+            out = dev.cpu().numpy()
+            crc = dcrc.cpu().numpy().view(np.uint32).reshape(ns, n)
+            for s in list(range(min(ns, 3))) + [ns - 1]:
+                sh = [host[s, i, :S].copy() for i in range(n)]
+                ora.encode(sh)
+                for i in range(n):
+                    assert (out[s, i, :S] == sh[i]).all(), (k, m, S, s, i)
+                    assert crc[s, i] == oracle.crc32(sh[i].tobytes(), poly), (k, m, S, s, i, poly)
+
+
 def test_bitsliced_verify_kernel(cb):
     """rs_bs_kernel<verify> (reedSolomon.Verify, RS/reedsolomon.go:770-784): ok on encoded stripes;
     one flipped bit in any parity OR data shard -- first byte, last byte, middle -- fails exactly that
