@@ -82,6 +82,20 @@ struct Lane {
   size_t h_aux_cap = 0;
 };
 
+// Stream-ordered scratch that is released on EVERY exit path of the function that allocated it (the
+// free is enqueued behind the kernels already launched on the stream).
+struct AsyncScratch {
+  cudaStream_t stream;
+  void* ptr = nullptr;
+  explicit AsyncScratch(cudaStream_t s) : stream(s) {}
+  AsyncScratch(const AsyncScratch&) = delete;
+  AsyncScratch& operator=(const AsyncScratch&) = delete;
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&ptr, bytes, stream); }
+  ~AsyncScratch() {
+    if (ptr) cudaFreeAsync(ptr, stream);
+  }
+};
+
 struct DevCtx {
   int device = 0;
   int sm_count = 0;
@@ -650,10 +664,10 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
     const bool ws = want_crc && g_force_kernel.load() == 5 && h->bs_passes == 1 && bsw_supported(h->k, h->m) &&
                     !bs_is_packed(shard_len);
     const Geometry gm = ws ? pick_geometry(c, shard_len, n_stripes, false, kBswTile) : bs_geometry(c, shard_len, n_stripes);
-    bool own = false;
+    AsyncScratch scratch(stream);
     if (want_crc && !d_part) {
-      CU(cudaMallocAsync(&d_part, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
-      own = true;
+      CU(scratch.alloc(n_stripes * n * gm.n_seg * sizeof(uint32_t)));
+      d_part = static_cast<uint32_t*>(scratch.ptr);
     }
     if (want_crc && gm.packed_pps) CU(cudaMemsetAsync(d_part, 0, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
     const bool rolled = want_crc && g_force_kernel.load() == 6 && !gm.packed_pps && bs_rolled_supported(h->k, h->m);
@@ -663,7 +677,6 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
     if (want_crc) {
       rc = finalize_crc(c, stream, d_part, n_stripes, n, shard_len, gm, crc_poly, nullptr, d_crc_out);
       if (rc) return rc;
-      if (own) CU(cudaFreeAsync(d_part, stream));
     }
     return CUBEEC_OK;
   }
@@ -677,10 +690,10 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
     nin.push_back(passes[j].n_in);
     ncrc.push_back((passes[j].crc_in ? passes[j].n_in : 0) + passes[j].n_out);
   }
-  bool own = false;
+  AsyncScratch scratch(stream);
   if (want_crc && !d_part) {
-    CU(cudaMallocAsync(&d_part, n_stripes * n * gm.n_seg * sizeof(uint32_t), stream));
-    own = true;
+    CU(scratch.alloc(n_stripes * n * gm.n_seg * sizeof(uint32_t)));
+    d_part = static_cast<uint32_t*>(scratch.ptr);
   }
   const std::vector<char> exact(pp.size(), 1);
   int rc = run_passes(c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, n, pp, nin, ncrc, exact, nullptr,
@@ -689,7 +702,6 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
   if (want_crc) {
     rc = finalize_crc(c, stream, d_part, n_stripes, n, shard_len, gm, crc_poly, nullptr, d_crc_out);
     if (rc) return rc;
-    if (own) CU(cudaFreeAsync(d_part, stream));
   }
   return CUBEEC_OK;
 }
@@ -886,10 +898,10 @@ int dev_lrc_encode_impl(cubeec* hg, cubeec* hl, const LrcLayout& y, DevCtx& c, c
   }
   const bool want_crc = d_crc_out != nullptr;
   const Geometry gm = bs_geometry(c, shard_len, n_stripes);
-  bool own = false;
+  AsyncScratch scratch(stream);
   if (want_crc && !d_part) {
-    CU(cudaMallocAsync(&d_part, n_stripes * n_slots * gm.n_seg * sizeof(uint32_t), stream));
-    own = true;
+    CU(scratch.alloc(n_stripes * n_slots * gm.n_seg * sizeof(uint32_t)));
+    d_part = static_cast<uint32_t*>(scratch.ptr);
   }
   if (want_crc && gm.packed_pps) CU(cudaMemsetAsync(d_part, 0, n_stripes * n_slots * gm.n_seg * sizeof(uint32_t), stream));
   int rc = bs_run(hg, c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, gm, n_slots, nullptr, y.N,
@@ -907,7 +919,6 @@ int dev_lrc_encode_impl(cubeec* hg, cubeec* hl, const LrcLayout& y, DevCtx& c, c
   if (want_crc) {
     rc = finalize_crc(c, stream, d_part, n_stripes, n_slots, shard_len, gm, crc_poly, nullptr, d_crc_out);
     if (rc) return rc;
-    if (own) CU(cudaFreeAsync(d_part, stream));
   }
   return CUBEEC_OK;
 }
@@ -1513,10 +1524,10 @@ int dev_crc32_impl(DevCtx& c, cudaStream_t st, const uint8_t* d_base, size_t len
   const size_t unit = block ? block : std::min<size_t>(len, 1u << 16);
   const size_t units = (len + unit - 1) / unit;
   uint32_t* d_units = d_blocks;
-  bool own = false;
+  AsyncScratch scratch(st);
   if (!d_units || !block) {
-    CU(cudaMallocAsync(&d_units, n_buffers * units * 4, st));
-    own = true;
+    CU(scratch.alloc(n_buffers * units * 4));
+    d_units = static_cast<uint32_t*>(scratch.ptr);
   }
   CrcRangeParams p;
   std::memset(&p, 0, sizeof(p));
@@ -1538,7 +1549,6 @@ int dev_crc32_impl(DevCtx& c, cudaStream_t st, const uint8_t* d_base, size_t len
                           g.poly[crc_poly ? 1 : 0].poly, d_whole, st));
     g_launches++;
   }
-  if (own) CU(cudaFreeAsync(d_units, st));
   return CUBEEC_OK;
 }
 }  // namespace
