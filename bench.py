@@ -4,12 +4,20 @@
 A "step" is one pass of the hot path over one batch of synthetic stripes:
   default workload  = BASELINE config C2: RS(12,4) encode + fused CRC32-IEEE of all 16 shards,
                       4 MiB blobs (shard 349,526 B, HBM pitch 349,568 B), 1024 stripes per GPU.
-  --workload reconstruct = config C3: same stripes, 3 random erasures per stripe.
+  --workload reconstruct = config C3 as the headline instead: same stripes, 3 random erasures per stripe.
 `value`  = device-resident whole-job data throughput (k*S*stripes / t), inputs already in HBM.
+`extra`  = (N=1) the other kernels of BASELINE's "encode + reconstruct" metric measured in the same run, same
+           batch: plain encode, verify, C3 reconstruct (3 random erasures per stripe), single-pattern repair
+           (one broken shard index for the whole batch), each with ms / data GiB/s / roofline fraction / kernel.
+`checked_stripes` = stripes of the TIMED batch compared with the CPU oracle after the timed region (parity bytes,
+           all 16 CRCs, reconstructed shards): first, last and seeded random ones.  A mismatch aborts the run.
 `e2e`    = the same metric through the C-ABI host entry point cubeec_encode_contig on pinned HOST
            buffers (H2D of the data shards and D2H of parity + CRCs inside the timed region).
+`e2e_single_call` = how access actually calls the codec (blobstore/common/ec/encoder.go:114-131): T host threads,
+           each encoding ONE 4 MiB blob per cubeec_encode call from pageable memory; the engine's coalescing
+           queue forms the batches.  Stripes/s, GiB/s and p50/p99 call latency.
 `roofline` = algorithmic bytes ((k+m)*S per stripe for encode, (k+e)*S for reconstruct) / device time
-           against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+           against the measured HBM copy bandwidth in MEASURED_PEAKS.json (and the nominal 8 TB/s).
 `cpu_baseline` = the oracle's multi-threaded SIMD port (AVX2 nibble tables / GFNI as klauspost would
            select, + PCLMUL CRC32) on this box's host cores, bounded sample.
 
@@ -23,6 +31,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -32,17 +41,23 @@ sys.path.insert(0, ROOT)
 K, M = 12, 4
 BLOB = 4 << 20
 GIB = float(1 << 30)
+NOMINAL_HBM_GBS = 8000.0   # B200 HBM3e spec ceiling (BASELINE.md section 3 asks for both fractions)
 
 
 def shard_size(blob, k, min_shard=2048):
     return max((blob + k - 1) // k, min_shard)   # blobstore/common/ec/buf.go:77-81
 
 
-def measured_traffic(kernel: str, stripes: int):
-    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the ncu --set full
-    capture summarised under profiles/ (taken at 1024 stripes; scaled linearly to this batch)."""
-    name = {"rs_bs_kernel<crc>": "r01_prof_r1_bs_crc.txt", "rs_bs_kernel": "r01_prof_r1_bs_nocrc.txt",
-            "rs_tabk_kernel": "r01_prof_tabk_rec.txt"}.get(kernel)
+PROFILE_OF_KERNEL = {"rs_bsf_kernel<crc>": "r02_prof_bsf_crc.txt", "rs_bs_kernel<crc>": "r01_prof_r1_bs_crc.txt",
+                     "rs_bs_kernel": "r02_prof_bs_nocrc.txt", "rs_tabk_kernel": "r01_prof_tabk_rec.txt",
+                     "rs_bsg_kernel": "r02_prof_bsg_rec.txt"}
+
+
+def traffic_from_profile(kernel: str, stripes: int):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, read from the committed ncu
+    --set full summary under profiles/ (taken at 1024 stripes; scaled linearly to this batch).  NOT measured in
+    this run -- a profiler run is never a bench value -- hence the field name."""
+    name = PROFILE_OF_KERNEL.get(kernel)
     try:
         txt = open(os.path.join(ROOT, "profiles", name)).read()
         tot = 0.0
@@ -51,9 +66,9 @@ def measured_traffic(kernel: str, stripes: int):
                 if line.startswith(key + " "):
                     val, unit = line.split()[1], line.split()[2]
                     tot += float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
-        return int(tot * stripes / 1024) if tot else None
+        return (int(tot * stripes / 1024), "profiles/" + name) if tot else (None, None)
     except Exception:
-        return None
+        return None, None
 
 
 def measured_peak():
@@ -104,57 +119,96 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(workload, stripes_sample, target_seconds=12.0):
-    """Oracle SIMD port on the host cores (bounded sample).  Returns (GiB/s of data, dict)."""
-    from oracle import pyoracle
-    S = shard_size(BLOB, K)
-    n = K + M
-    rs = pyoracle.RS(K, M)
-    rng = np.random.default_rng(0xC0BEF5)
-    buf = rng.integers(0, 256, (stripes_sample, n, S), dtype=np.uint8)
-    cores = os.cpu_count() or 1
-    crc = np.zeros((stripes_sample, n), dtype=np.uint32)
-    present = np.ones((stripes_sample, n), dtype=np.uint8)
-    if workload == "reconstruct":
-        rs.encode_batch_simd(buf, S, S, n * S, stripes_sample, threads=cores)
-        for s in range(stripes_sample):
-            present[s, rng.choice(n, size=3, replace=False)] = 0
-    threads = [cores]
-    REP = 4   # passes per call, so thread start-up is amortised
+# ---------------------------------------------------------------------------------------------------------
+# NUMA: pin this rank's host threads (and therefore its first-touch pinned buffers) to the GPU's node
+# ---------------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa_node(local_rank: int):
+    """SURVEY 8e "host threads pinned per device": the 8-GPU boxes are 2-socket; a rank whose staging buffers sit
+    on the other socket pays the inter-socket link on every H2D/D2H.  Returns a description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank)
+        pci = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{pci}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "single node / not reported"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return {"numa_node": node, "note": "node CPUs not in this process's affinity mask; left unpinned"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed), "pci": pci}
+    except Exception as e:   # noqa: BLE001
+        return {"numa_node": None, "note": f"unpinned ({type(e).__name__})"}
 
-    def one():
-        if workload == "encode":
-            rs.encode_batch_simd(buf, S, S, n * S, stripes_sample, threads=threads[0], crc_out=crc, repeat=REP)
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle's SIMD port): cpu_baseline of the GPU arm and the whole reference arm
+# ---------------------------------------------------------------------------------------------------------
+class CpuLeg:
+    def __init__(self, workload, stripes_sample):
+        from oracle import pyoracle
+        self.workload, self.sample = workload, stripes_sample
+        self.S = shard_size(BLOB, K)
+        self.n = K + M
+        self.rs = pyoracle.RS(K, M)
+        rng = np.random.default_rng(0xC0BEF5)
+        self.buf = rng.integers(0, 256, (stripes_sample, self.n, self.S), dtype=np.uint8)
+        self.crc = np.zeros((stripes_sample, self.n), dtype=np.uint32)
+        self.present = np.ones((stripes_sample, self.n), dtype=np.uint8)
+        self.cores = os.cpu_count() or 1
+        if workload == "reconstruct":
+            self.rs.encode_batch_simd(self.buf, self.S, self.S, self.n * self.S, stripes_sample, threads=self.cores)
+            for s in range(stripes_sample):
+                self.present[s, rng.choice(self.n, size=3, replace=False)] = 0
+        self.REP = 4   # passes per call, so thread start-up is amortised
+        self.threads = self.cores
+        self._tune()
+
+    def one(self):
+        if self.workload == "encode":
+            self.rs.encode_batch_simd(self.buf, self.S, self.S, self.n * self.S, self.sample, threads=self.threads,
+                                      crc_out=self.crc, repeat=self.REP)
         else:
-            rs.reconstruct_batch_simd(buf, S, S, n * S, stripes_sample, present, threads=threads[0], repeat=REP)
+            self.rs.reconstruct_batch_simd(self.buf, self.S, self.S, self.n * self.S, self.sample, self.present,
+                                           threads=self.threads, repeat=self.REP)
 
-    # the container may expose more CPUs than it may use: pick the thread count that is fastest
-    best = None
-    for th in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 32), min(cores, 16), min(cores, 8)}):
-        threads[0] = th
-        one()
-        t0 = time.perf_counter()
-        one()
-        dt = time.perf_counter() - t0
-        if best is None or dt < best[0]:
-            best = (dt, th)
-    threads[0] = best[1]
-    cores = best[1]
+    def _tune(self):
+        # the container may expose more CPUs than it may use: pick the thread count that is fastest
+        best = None
+        c = self.cores
+        for th in sorted({c, max(1, c // 2), max(1, c // 4), min(c, 32), min(c, 16), min(c, 8)}):
+            self.threads = th
+            self.one()
+            t0 = time.perf_counter()
+            self.one()
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, th)
+        self.threads = best[1]
+
+    def describe(self):
+        return (f"oracle SIMD port ({self.rs.simd_kind()} GF kernels as klauspost v1.11.7 selects for k={K}; "
+                f"PCLMUL CRC32-IEEE), one stripe per thread, {self.threads} threads")
+
+
+def cpu_baseline(workload, stripes_sample, target_seconds=12.0):
+    leg = CpuLeg(workload, stripes_sample)
     t0 = time.perf_counter()
     reps = 0
     while True:
-        one()
+        leg.one()
         reps += 1
         el = time.perf_counter() - t0
         if el >= target_seconds or reps >= 200:
             break
-    reps *= REP
-    gibs = K * S * stripes_sample * reps / el / GIB
-    info = {"value": round(gibs, 3), "unit": "GiB/s", "cores": cores, "kind": "port",
-            "sample": f"{stripes_sample} stripes x {reps} passes, {el:.1f} s, oracle SIMD port "
-                      f"({rs.simd_kind()} GF kernels as klauspost v1.11.7 selects for k={K}; PCLMUL CRC32-IEEE), "
-                      f"one stripe per thread over all cores"}
-    return gibs, info, el / reps
+    reps *= leg.REP
+    gibs = K * leg.S * stripes_sample * reps / el / GIB
+    return {"value": round(gibs, 3), "unit": "GiB/s", "cores": leg.threads, "kind": "port",
+            "sample": f"{stripes_sample} stripes x {reps} passes, {el:.1f} s, {leg.describe()}"}
 
 
 def run_reference(args, rank, world):
@@ -162,59 +216,23 @@ def run_reference(args, rank, world):
     (no toolchain here), so this is the oracle's SIMD port on all host cores; rank 0 only."""
     if rank != 0:
         return
-    sample = args.cpu_stripes
-    steps_s = []
-    # each "step" is one pass over the bounded sample
-    from oracle import pyoracle
-    S = shard_size(BLOB, K)
-    n = K + M
-    rs = pyoracle.RS(K, M)
-    rng = np.random.default_rng(0xC0BEF5)
-    buf = rng.integers(0, 256, (sample, n, S), dtype=np.uint8)
-    cores = os.cpu_count() or 1
-    crc = np.zeros((sample, n), dtype=np.uint32)
-    present = np.ones((sample, n), dtype=np.uint8)
-    if args.workload == "reconstruct":
-        rs.encode_batch_simd(buf, S, S, n * S, sample, threads=cores)
-        for s in range(sample):
-            present[s, rng.choice(n, size=3, replace=False)] = 0
-
-    REP = 4   # a step = REP passes over the bounded sample (thread start-up amortised)
-    threads = [cores]
-
-    def one():
-        if args.workload == "encode":
-            rs.encode_batch_simd(buf, S, S, n * S, sample, threads=threads[0], crc_out=crc, repeat=REP)
-        else:
-            rs.reconstruct_batch_simd(buf, S, S, n * S, sample, present, threads=threads[0], repeat=REP)
-
-    # the container may expose more CPUs than it may use: pick the fastest thread count
-    best = None
-    for th in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 32), min(cores, 16), min(cores, 8)}):
-        threads[0] = th
-        one()
-        t0 = time.perf_counter()
-        one()
-        dt = time.perf_counter() - t0
-        if best is None or dt < best[0]:
-            best = (dt, th)
-    threads[0] = cores = best[1]
+    leg = CpuLeg(args.workload, args.cpu_stripes)
     for _ in range(args.warmup):
-        one()
+        leg.one()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        one()
+        leg.one()
     el = time.perf_counter() - t0
-    sample_total = sample * REP
-    gibs = K * S * sample_total * args.steps / el / GIB
+    sample_total = leg.sample * leg.REP
+    gibs = K * leg.S * sample_total * args.steps / el / GIB
     line = base_line(args, world, gibs, el / args.steps * 1e3)
     line["impl"] = "reference"
     line["n_gpus"] = args.gpus
-    line["cpu_baseline"] = {"value": round(gibs, 3), "unit": "GiB/s", "cores": cores, "kind": "port",
-                            "sample": f"{sample_total} stripes per step ({sample} distinct), oracle SIMD port ({rs.simd_kind()}), {cores} threads"}
+    line["cpu_baseline"] = {"value": round(gibs, 3), "unit": "GiB/s", "cores": leg.threads, "kind": "port",
+                            "sample": f"{sample_total} stripes per step ({leg.sample} distinct, bounded sample of the "
+                                      f"config's batch), {leg.describe()}"}
     line["e2e"] = {"value": round(gibs, 3), "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     line["gpu_launches"] = 0
-    line["config"]["stripes_per_step"] = sample_total
     print(json.dumps(line), flush=True)
 
 
@@ -233,6 +251,9 @@ def base_line(args, world, value, ms_per_step):
     }
 
 
+# ---------------------------------------------------------------------------------------------------------
+# the GPU arm
+# ---------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -245,8 +266,10 @@ def main():
     ap.add_argument("--cpu-stripes", type=int, default=256, help="stripes in the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "table", "ws", "bsrec", "rolled"],
-                    help="A/B aid: table = generic table kernel, ws = warp-specialised fused encode+CRC kernel")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--force", type=int, default=0, help="cubeec_debug_force_kernel value (A/B aid, see include/cubeec.h)")
+    ap.add_argument("--single-threads", default="64,256,1000", help="caller threads of the e2e_single_call record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -267,17 +290,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: cubefs_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = pin_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cb.init([local_rank])
-    if args.kernel == "table":
-        cb.force_kernel(1)
-    if args.kernel == "ws":
-        cb.force_kernel(5)
-    if args.kernel == "bsrec":
-        cb.force_kernel(2)
-    if args.kernel == "rolled":
-        cb.force_kernel(6)
+    if args.force:
+        cb.force_kernel(args.force)
 
     # coding matrix: built on rank 0, NCCL-broadcast to the other ranks (the only shared state)
     if rank == 0:
@@ -298,28 +316,88 @@ def main():
     for s0 in range(0, ns, 64):
         batch[s0:s0 + 64] = torch.randint(0, 256, batch[s0:s0 + 64].shape, dtype=torch.uint8, device=dev, generator=g)
     dcrc = torch.zeros(ns * n, dtype=torch.int32, device=dev)
+    dok = torch.zeros(ns, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
     rng = np.random.default_rng(0xC0BEF5 + rank)
-    present = np.ones((ns, n), dtype=np.uint8)
-    erasures = 0
-    if args.workload == "reconstruct":
-        eng.dev_encode(batch.data_ptr(), S, P, n * P, ns, stream=stream, device=local_rank)
-        for s in range(ns):
-            present[s, rng.choice(n, size=3, replace=False)] = 0
-        erasures = 3
-
-    def step():
-        if args.workload == "encode":
-            eng.dev_encode(batch.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr() if args.crc else 0,
-                           stream=stream, device=local_rank)
-        else:
-            eng.dev_reconstruct(batch.data_ptr(), S, P, n * P, ns, present, stream=stream, device=local_rank)
+    present3 = np.ones((ns, n), dtype=np.uint8)
+    for s in range(ns):
+        present3[s, rng.choice(n, size=3, replace=False)] = 0
+    present1 = np.ones((ns, n), dtype=np.uint8)
+    present1[:, 3] = 0   # one broken vuid: the same shard index missing in every stripe (worker_slice_recover.go:822-871)
+    sample_ids = sorted({0, ns - 1, *[int(x) for x in rng.choice(ns, size=min(6, ns), replace=False)]})
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def enc(crc=True):
+        eng.dev_encode(batch.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr() if crc else 0, stream=stream, device=local_rank)
+
+    def rec(present):
+        eng.dev_reconstruct(batch.data_ptr(), S, P, n * P, ns, present, stream=stream, device=local_rank)
+
+    def ver():
+        eng.dev_verify(batch.data_ptr(), S, P, n * P, ns, dok.data_ptr(), stream=stream, device=local_rank)
+
+    def erase(present):
+        """overwrite the shards a reconstruct has to regenerate, so a step that did nothing cannot pass the check"""
+        rows_, cols_ = np.nonzero(present == 0)
+        batch[torch.from_numpy(rows_).to(dev), torch.from_numpy(cols_).to(dev)] = 0xA5
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / steps
+
+    # ---- oracle checks on sampled stripes of the timed batch -------------------------------------------------
+    def host_stripe(s):
+        return batch[s, :, :S].cpu().numpy()
+
+    def check_encode(with_crc):
+        from oracle import pyoracle
+        rs = pyoracle.RS(K, M)
+        crcs = dcrc.cpu().numpy().view(np.uint32).reshape(ns, n)
+        for s in sample_ids:
+            h = host_stripe(s)
+            want = [h[i].copy() for i in range(K)] + [np.zeros(S, np.uint8) for _ in range(M)]
+            rs.encode(want)
+            for i in range(K, n):
+                if not np.array_equal(h[i], want[i]):
+                    raise SystemExit(f"bench check FAILED: parity shard {i} of stripe {s} differs from the oracle")
+            if with_crc:
+                for i in range(n):
+                    if int(crcs[s, i]) != zlib.crc32(want[i].tobytes()):
+                        raise SystemExit(f"bench check FAILED: CRC of shard {i} of stripe {s} differs from zlib")
+        return len(sample_ids)
+
+    def check_reconstruct(originals, present):
+        for s in sample_ids:
+            h = host_stripe(s)
+            for i in np.nonzero(present[s] == 0)[0]:
+                if not np.array_equal(h[i], originals[s][i]):
+                    raise SystemExit(f"bench check FAILED: reconstructed shard {i} of stripe {s} differs from the original")
+        return len(sample_ids)
+
+    # ---- headline -------------------------------------------------------------------------------------------
+    peak, peak_src = measured_peak()
+    enc(True)
+    barrier()
+    originals = None if args.no_check else {s: host_stripe(s) for s in sample_ids}   # encoded stripes (oracle-checked below)
+    erasures = 0
+    if args.workload == "reconstruct":
+        erase(present3)
+        erasures = 3
+        step = lambda: rec(present3)   # noqa: E731
+    else:
+        step = lambda: enc(bool(args.crc))   # noqa: E731
     for _ in range(args.warmup):
         step()
     barrier()
@@ -336,23 +414,60 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = cb.kernel_launches() - launches0
+    head_kernel = cb.last_kernel()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ms_step = ms / args.steps
+    ms_step = float(t.item()) / args.steps
     value = K * S * ns * world / (ms_step * 1e-3) / GIB
+    checked = 0
+    if not args.no_check:
+        checked = check_reconstruct(originals, present3) if args.workload == "reconstruct" else check_encode(bool(args.crc))
 
-    # ---- end to end through the host entry point (pinned host buffers) ----
+    def record(ms_, alg_bytes, kernel):
+        ach = alg_bytes / (ms_ * 1e-3) / 1e9
+        return {"ms": round(ms_, 4), "data_GiB_per_s": round(K * S * ns / (ms_ * 1e-3) / GIB, 1), "achieved_GBps": round(ach, 1),
+                "frac": round(ach / peak, 4), "frac_nominal_8TBs": round(ach / NOMINAL_HBM_GBS, 4), "kernel": kernel,
+                "algorithmic_bytes": alg_bytes}
+
+    # ---- the rest of "encode + reconstruct": plain encode, verify, C3, single-pattern repair (N = 1 only) ----------
+    extra = None
+    if world == 1 and not args.no_extra:
+        extra = {}
+        st, wu = max(3, min(args.steps, 5)), 3
+        if args.workload == "reconstruct":
+            rec(present3)   # leave the batch consistent
+        ms_ = timed(lambda: enc(False), st, wu)
+        extra["encode_nocrc"] = record(ms_, n * S * ns, cb.last_kernel())
+        ms_ = timed(lambda: enc(True), st, wu)
+        extra["encode_crc"] = record(ms_, n * S * ns, cb.last_kernel())
+        ms_ = timed(ver, st, wu)
+        extra["verify"] = record(ms_, n * S * ns, cb.last_kernel())
+        if not args.no_check and int(dok.sum().item()) != ns:
+            raise SystemExit("bench check FAILED: dev_verify rejects a stripe the engine just encoded")
+        for name, pres, e in (("reconstruct_3e", present3, 3), ("reconstruct_1pattern", present1, 1)):
+            erase(pres)
+            ms_ = timed(lambda pres=pres: rec(pres), st, wu)
+            extra[name] = record(ms_, (K + e) * S * ns, cb.last_kernel())
+            extra[name]["patterns"] = int(len({bytes(r) for r in pres}))
+            if not args.no_check:
+                extra[name]["checked_stripes"] = check_reconstruct(originals, pres)
+        extra["note"] = (f"same 1024-stripe batch, {st} timed steps after {wu} warm-up each, CUDA events; reconstruct regenerates "
+                         "shards that were overwritten with 0xA5 first; algorithmic bytes: encode/verify (k+m)*S, reconstruct (k+e)*S")
+
+    # ---- end to end through the host entry points (pinned host buffers; then single-stripe pageable calls) ----
     e2e = None
+    e2e_single = None
     if not args.no_e2e and args.workload == "encode":
+        del batch
+        torch.cuda.empty_cache()
         ns_e = min(ns, 512)
         host = torch.empty((ns_e, n * S), dtype=torch.uint8).pin_memory()
         host.copy_(torch.randint(0, 256, host.shape, dtype=torch.uint8))
         hnp = host.numpy()
         for _ in range(2):
-            eng.encode_contig(hnp, S, ns_e, n * S, crc=bool(args.crc))
+            crc_h, _ = eng.encode_contig(hnp, S, ns_e, n * S, crc=bool(args.crc))
         barrier()
         t0 = time.perf_counter()
         reps = max(2, min(args.steps, 5))
@@ -366,24 +481,44 @@ def main():
         el = float(t.item())
         e2e = {"value": round(K * S * ns_e * world * reps / el / GIB, 3), "unit": "GiB/s",
                "h2d_bytes_per_step": K * S * ns_e, "d2h_bytes_per_step": M * S * ns_e + (n * ns_e * 4 if args.crc else 0),
-               "stripes_per_step": ns_e, "api": "cubeec_encode_contig (pinned host ec.Buffer layout, H2D+kernel+D2H pipelined)"}
+               "stripes_per_step": ns_e, "numa": numa,
+               "api": "cubeec_encode_contig (pinned host ec.Buffer layout, H2D+kernel+D2H pipelined)"}
+        if not args.no_check:
+            from oracle import pyoracle
+            rs = pyoracle.RS(K, M)
+            for s in (0, ns_e - 1):
+                row = hnp[s].reshape(n, S)
+                want = [row[i].copy() for i in range(K)] + [np.zeros(S, np.uint8) for _ in range(M)]
+                rs.encode(want)
+                ok = all(np.array_equal(row[i], want[i]) for i in range(n))
+                ok = ok and (crc_h is None or all(int(crc_h[s, i]) == zlib.crc32(want[i].tobytes()) for i in range(n)))
+                if not ok:
+                    raise SystemExit(f"bench check FAILED: e2e stripe {s} differs from the oracle")
+            e2e["checked_stripes"] = 2
+        if world == 1 and hasattr(eng, "encode_single_call_bench"):
+            e2e_single = eng.encode_single_call_bench(BLOB, [int(x) for x in args.single_threads.split(",")],
+                                                      check=not args.no_check)
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         alg = ((K + M) if args.workload == "encode" else (K + erasures)) * S * ns
         achieved = alg / (ms_step * 1e-3) / 1e9
         line = base_line(args, world, value, ms_step)
         line["clocks"] = clocks
         line["gpu_launches"] = int(launches)
-        line["kernel"] = cb.last_kernel()
+        line["kernel"] = head_kernel
+        line["checked_stripes"] = checked
+        traffic, traffic_src = traffic_from_profile(head_kernel, ns)
         line["roofline"] = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                            "frac": round(achieved / peak, 4), "traffic": measured_traffic(cb.last_kernel(), ns), "peak_source": peak_src,
+                            "frac": round(achieved / peak, 4), "frac_nominal_8TBs": round(achieved / NOMINAL_HBM_GBS, 4),
+                            "traffic": traffic, "traffic_from_profile": traffic_src, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": alg,
-                            "note": "per-GPU figure; device time of one step (coding kernel + CRC finalize) by CUDA events"}
+                            "note": "per-GPU figure; device time of one step (coding kernel + CRC finalize) by CUDA events; "
+                                    "traffic is read from the committed ncu summary named in traffic_from_profile, not measured in this run"}
+        line["extra"] = extra
         line["e2e"] = e2e
+        line["e2e_single_call"] = e2e_single
         if world == 1 and not args.no_cpu:
-            _, info, _ = cpu_baseline(args.workload, args.cpu_stripes)
-            line["cpu_baseline"] = info
+            line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_stripes)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

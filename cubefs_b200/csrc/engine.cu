@@ -109,6 +109,9 @@ struct DevCtx {
   // the same two for the tile of the warp-specialised kernel (bitslice_ws.cu)
   uint32_t* d_bsw_fold[2] = {nullptr, nullptr};
   uint32_t* d_bsw_kthread[2] = {nullptr, nullptr};
+  // flat-split fused kernel (bs_flat.cuh): Horner step between a lane's pieces of consecutive units, lane alignment
+  uint32_t* d_bsf_fold[2] = {nullptr, nullptr};
+  uint32_t* d_bsf_klane[2] = {nullptr, nullptr};
   std::mutex mu;
   std::condition_variable cv;
   std::vector<Lane*> free_lanes;
@@ -177,6 +180,13 @@ int setup_device(DevCtx& c) {
     CU(cudaMemcpy(c.d_bsw_fold[pi], fold, sizeof(fold), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c.d_bsw_kthread[pi], kth.size() * 4));
     CU(cudaMemcpy(c.d_bsw_kthread[pi], kth.data(), kth.size() * 4, cudaMemcpyHostToDevice));
+    crc_const_mul_tables(P, P.shift_bytes_const((int64_t)kBsfUnitBytes - kBsPiece), fold);
+    uint32_t klane[32];
+    for (int l = 0; l < 32; l++) klane[l] = P.shift_bytes_const((int64_t)kBsPiece * (31 - l));
+    CU(cudaMalloc(&c.d_bsf_fold[pi], sizeof(fold)));
+    CU(cudaMemcpy(c.d_bsf_fold[pi], fold, sizeof(fold), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c.d_bsf_klane[pi], sizeof(klane)));
+    CU(cudaMemcpy(c.d_bsf_klane[pi], klane, sizeof(klane), cudaMemcpyHostToDevice));
   }
   return CUBEEC_OK;
 }
@@ -557,15 +567,6 @@ size_t ctx_index(const DevCtx* c) {
   return 0;
 }
 
-// Bytes of CRC scratch (per-segment remainders) an encode of this geometry needs.
-size_t crc_part_bytes(const DevCtx& c, size_t shard_len, size_t n_stripes, int n_slots) {
-  // upper bound over both kernels' geometries
-  const Geometry g1 = pick_geometry(c, shard_len, n_stripes, false);
-  const Geometry g2 = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
-  const Geometry g3 = pick_geometry(c, shard_len, n_stripes, false, kBswTile);
-  return n_stripes * (size_t)n_slots * std::max<uint32_t>(std::max(std::max(g1.n_seg, g2.n_seg), g3.n_seg), 2u) * sizeof(uint32_t);
-}
-
 // The bit-sliced kernel needs 32-byte columns: base and pitches 32-aligned, room for whole groups.
 bool bs_layout_ok(const uint8_t* d_base, size_t shard_len, size_t shard_pitch, size_t stripe_pitch) {
   return (((uintptr_t)d_base | shard_pitch | stripe_pitch) & 31) == 0 && shard_pitch >= round_up(shard_len, 32);
@@ -650,6 +651,122 @@ int bs_run(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t sh
   return CUBEEC_OK;
 }
 
+// ---- flat work split of the fused encode + CRC kernel (bs_flat.cuh) ----------------------------------
+struct FlatGeometry {
+  uint32_t units_per_shard = 0;
+  uint64_t total_units = 0, total_warps = 0;
+  uint32_t max_parts = 0;
+  int grid = 0, threads = kBsfThreads;
+};
+
+int bsf_threads() {
+  const int f = g_force_kernel.load();
+  return (f >= 1000 && f < 2000) ? f - 1000 : kBsfThreads;   // cubeec_debug_force_kernel(1000 + threads): A/B aid
+}
+
+FlatGeometry flat_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes) {
+  FlatGeometry fg;
+  fg.threads = bsf_threads();
+  const uint64_t nw = (uint64_t)fg.threads / 32;
+  fg.units_per_shard = (uint32_t)((shard_len + kBsfUnitBytes - 1) / kBsfUnitBytes);
+  fg.total_units = (uint64_t)n_stripes * fg.units_per_shard;
+  fg.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((fg.total_units + nw - 1) / nw, (uint64_t)c.sm_count));
+  fg.total_warps = (uint64_t)fg.grid * nw;
+  // runs that can touch one stripe (part slots per shard): runs are floor(U/GW) or one more units long
+  const uint64_t U = fg.total_units, GW = fg.total_warps, wt = fg.units_per_shard;
+  if (U >= GW) fg.max_parts = (uint32_t)((wt - 1) / (U / GW) + 2);
+  else fg.max_parts = (uint32_t)((wt * GW + U - 1) / U + 2);   // more warps than units: empty runs in between
+  return fg;
+}
+size_t flat_part_bytes(const FlatGeometry& fg, size_t n_stripes, int n_slots) {
+  return n_stripes * (size_t)n_slots * fg.max_parts * sizeof(uint32_t);
+}
+// Is the flat kernel the path for this (handle, layout)?  Shards of at least 16 KiB (smaller ones: packed mode
+// of rs_bs_kernel), every pass of the code instantiated.
+bool flat_usable(const cubeec* h, size_t shard_len, int first_pass_mode) {
+  const int f = g_force_kernel.load();
+  if (f == 5 || f == 6 || f == 7 || !h->bs_passes || shard_len < 16384) return false;   // 5/6/7: the tile-split variants
+  for (int pass = 0; pass < h->bs_passes; pass++)
+    if (!bsf_supported(h->k, h->m, pass, pass == 0 ? first_pass_mode : 2)) return false;
+  return true;
+}
+
+// All fused-CRC passes of handle h (crc: 1 = data + outputs in the first pass, 2 = outputs only) with the flat split.
+int bsf_run(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t shard_len, size_t shard_pitch,
+            size_t stripe_pitch, size_t n_stripes, const FlatGeometry& fg, int n_slots, const uint8_t* in_slots, int out_first,
+            int crc, uint32_t* d_part, int crc_poly) {
+  BsfParams bp;
+  std::memset(&bp, 0, sizeof(bp));
+  bp.base = d_base;
+  bp.stripe_pitch = stripe_pitch;
+  bp.shard_pitch = shard_pitch;
+  bp.shard_len = (uint32_t)shard_len;
+  bp.n_stripes = (uint32_t)n_stripes;
+  bp.n_slots = (uint32_t)n_slots;
+  bp.units_per_shard = fg.units_per_shard;
+  bp.total_units = fg.total_units;
+  bp.max_parts = fg.max_parts;
+  bp.crc_part = d_part;
+  const int pi = crc_poly ? 1 : 0;
+  bp.poly = g.poly[pi].poly;
+  bp.slice_image = c.d_bs_slice[pi];
+  bp.fold_tables = c.d_bsf_fold[pi];
+  bp.klane = c.d_bsf_klane[pi];
+  if (h->k > (int)sizeof(bp.in_slot)) return CUBEEC_ERR_UNSUPPORTED;
+  if (crc == 1 && in_slots) return CUBEEC_ERR_INVALID_ARG;   // data CRCs only with the identity input map
+  for (int i = 0; i < h->k; i++) bp.in_slot[i] = in_slots ? in_slots[i] : (uint8_t)i;
+  for (int pass = 0; pass < h->bs_passes; pass++) {
+    int r0 = 0, rows = h->m;
+    if (h->bs_passes > 1 || h->m > 4) {
+      if (!bs_mp_pass_rows(h->k, h->m, 0, pass, &r0, &rows)) return CUBEEC_ERR_UNSUPPORTED;
+    }
+    for (int r = 0; r < rows && r < (int)sizeof(bp.out_slot); r++) bp.out_slot[r] = (uint8_t)(out_first + r0 + r);
+    const int mode = (crc == 1 && pass == 0) ? 1 : 2;
+    if (fg.threads != kBsfThreads && h->k == 12 && h->m == 4 && mode == 1) CU(launch_bsf_variant(fg.threads, bp, fg.grid, stream));
+    else CU(launch_bsf(h->k, h->m, pass, mode, bp, fg.grid, stream));
+    g_launches++;
+  }
+  t_last_kernel = "rs_bsf_kernel<crc>";
+  return CUBEEC_OK;
+}
+
+int finalize_flat_crc(cudaStream_t stream, const uint32_t* d_part, size_t n_stripes, int n_slots, size_t shard_len,
+                      const FlatGeometry& fg, int crc_poly, uint32_t* d_out) {
+  const CrcPoly& P = g.poly[crc_poly ? 1 : 0];
+  CrcPartsFinalizeParams f;
+  std::memset(&f, 0, sizeof(f));
+  f.crc_part = d_part;
+  f.n_stripes = (uint32_t)n_stripes;
+  f.n_slots = (uint32_t)n_slots;
+  f.max_parts = fg.max_parts;
+  f.units_per_shard = fg.units_per_shard;
+  f.total_units = fg.total_units;
+  f.total_warps = fg.total_warps;
+  f.shard_len = (uint32_t)shard_len;
+  f.first_slot = 0;
+  f.n_out = (uint32_t)n_slots;
+  f.poly = P.poly;
+  for (int i = 0; i < 24; i++) f.x_unit_pow[i] = P.shift_bytes_const((int64_t)kBsfUnitBytes << i);
+  f.fix = P.shift_bytes_const(-((int64_t)fg.units_per_shard * kBsfUnitBytes - (int64_t)shard_len));
+  f.init_term = P.mul(0xFFFFFFFFu, P.shift_bytes_const((int64_t)shard_len));
+  f.out = d_out;
+  CU(launch_crc_parts_finalize(f, stream));
+  g_launches++;
+  return CUBEEC_OK;
+}
+
+// Bytes of CRC scratch (per-segment remainders) an encode of this geometry needs.
+size_t crc_part_bytes(const DevCtx& c, size_t shard_len, size_t n_stripes, int n_slots) {
+  // upper bound over both kernels' geometries
+  const Geometry g1 = pick_geometry(c, shard_len, n_stripes, false);
+  const Geometry g2 = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
+  const Geometry g3 = pick_geometry(c, shard_len, n_stripes, false, kBswTile);
+  const size_t tiled = n_stripes * (size_t)n_slots * std::max<uint32_t>(std::max(std::max(g1.n_seg, g2.n_seg), g3.n_seg), 2u) * sizeof(uint32_t);
+  size_t flat = 0;
+  if (shard_len >= 16384) flat = flat_part_bytes(flat_geometry(c, shard_len, n_stripes), n_stripes, n_slots);
+  return std::max(tiled, flat);
+}
+
 // Encode (mode 0) or verify (mode 1) a device-resident batch.  d_part: caller scratch of
 // crc_part_bytes() when CRCs are wanted, or nullptr to use the stream-ordered allocator.
 int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t shard_len,
@@ -660,7 +777,20 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
   const size_t ci = ctx_index(&c);
   const bool want_crc = mode == 0 && d_crc_out;
   if (h->bs_passes && g_force_kernel.load() != 1 && bs_layout_ok(d_base, shard_len, shard_pitch, stripe_pitch)) {
-    // hot path: bit-sliced XOR-network kernel (bitslice.cu)
+    if (want_crc && flat_usable(h, shard_len, 1)) {
+      // fused encode + CRC32 with the flat work split (bs_flat.cuh)
+      const FlatGeometry fg = flat_geometry(c, shard_len, n_stripes);
+      AsyncScratch fscratch(stream);
+      if (!d_part) {
+        CU(fscratch.alloc(flat_part_bytes(fg, n_stripes, n)));
+        d_part = static_cast<uint32_t*>(fscratch.ptr);
+      }
+      int rc = bsf_run(h, c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, fg, n, nullptr, h->k, 1, d_part,
+                       crc_poly);
+      if (rc) return rc;
+      return finalize_flat_crc(stream, d_part, n_stripes, n, shard_len, fg, crc_poly, d_crc_out);
+    }
+    // bit-sliced XOR-network kernel with the CTA-tile split (bitslice.cu): plain encode, verify, packed mode
     const bool ws = want_crc && g_force_kernel.load() == 5 && h->bs_passes == 1 && bsw_supported(h->k, h->m) &&
                     !bs_is_packed(shard_len);
     const Geometry gm = ws ? pick_geometry(c, shard_len, n_stripes, false, kBswTile) : bs_geometry(c, shard_len, n_stripes);
@@ -897,6 +1027,29 @@ int dev_lrc_encode_impl(cubeec* hg, cubeec* hl, const LrcLayout& y, DevCtx& c, c
     return CUBEEC_ERR_UNSUPPORTED;
   }
   const bool want_crc = d_crc_out != nullptr;
+  if (want_crc && flat_usable(hg, shard_len, 1) && flat_usable(hl, shard_len, 2)) {
+    // every code of the stripe with the flat split: the global passes checksum data + global parity, each
+    // AZ's local pass the local parity it writes; one finalize over all N+M+L slots
+    const FlatGeometry fg = flat_geometry(c, shard_len, n_stripes);
+    AsyncScratch fscratch(stream);
+    if (!d_part) {
+      CU(fscratch.alloc(flat_part_bytes(fg, n_stripes, n_slots)));
+      d_part = static_cast<uint32_t*>(fscratch.ptr);
+    }
+    int rc = bsf_run(hg, c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, fg, n_slots, nullptr, y.N, 1, d_part,
+                     crc_poly);
+    if (rc) return rc;
+    for (int a = 0; a < y.az; a++) {
+      uint8_t in_slots[64];
+      int q = 0;
+      for (int i = 0; i < y.N / y.az; i++) in_slots[q++] = (uint8_t)(a * (y.N / y.az) + i);
+      for (int i = 0; i < y.M / y.az; i++) in_slots[q++] = (uint8_t)(y.N + a * (y.M / y.az) + i);
+      rc = bsf_run(hl, c, stream, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, fg, n_slots, in_slots,
+                   y.N + y.M + a * y.ml, 2, d_part, crc_poly);
+      if (rc) return rc;
+    }
+    return finalize_flat_crc(stream, d_part, n_stripes, n_slots, shard_len, fg, crc_poly, d_crc_out);
+  }
   const Geometry gm = bs_geometry(c, shard_len, n_stripes);
   AsyncScratch scratch(stream);
   if (want_crc && !d_part) {
@@ -1396,8 +1549,10 @@ int encode_contig_device(cubeec* h, DevCtx* c, uint8_t* base, size_t S, size_t f
   size_t chunk = std::max<size_t>(1, (std::max<size_t>(chunk_mb, 1) << 20) / dstripe);
   chunk = std::min(chunk, count);
   const int n_lanes = std::max(1, std::min(lanes_env, 8));
-  // CRC scratch bound for any chunk of <= `chunk` stripes: nb * n_seg(nb) <= 8*SMs + nb
-  const size_t part_cap = round_up((size_t)n * (8 * (size_t)c->sm_count + chunk + 8) * 4, 256);
+  // CRC scratch: only two batch sizes occur, `chunk` and the remainder of the last chunk
+  size_t part_cap = crc_part_bytes(*c, S, chunk, n);
+  if (count % chunk) part_cap = std::max(part_cap, crc_part_bytes(*c, S, count % chunk, n));
+  part_cap = round_up(part_cap, 256);
   const size_t crc_cap = round_up(chunk * n * 4, 256);
   const size_t units = blockcrc_out ? (S + block_payload - 1) / block_payload : 0;
   const size_t blk_cap = round_up(chunk * n * units * 4, 256);

@@ -149,6 +149,49 @@ def emit_shard(lines, coefs, var_p="p", var_acc="acc"):
     return n_xor3
 
 
+N_PARTS = 5
+
+
+def emit_shard_parts(coefs):
+    """The same network as emit_shard, as N_PARTS statement lists for the software-pipelined kernel
+    (bs_flat.cuh): every XOR combination is created right before its first use (short live ranges) and the
+    outputs are visited grouped by their low-nibble combination.  Combinations live in t[]: t[x] = XOR of
+    the planes 0..3 selected by x, t[16 + x] = the same for planes 4..7."""
+    uses = []
+    for r, c in enumerate(coefs):
+        for i, mk in enumerate(row_masks(c)):
+            if mk:
+                uses.append((mk & 15, mk >> 4, r * 8 + i))
+    uses.sort()
+    built = set()
+    stmts = []
+
+    def name(x, base):
+        if x & (x - 1) == 0:
+            return f"p[{base + x.bit_length() - 1}]"
+        return f"t[{(16 if base else 0) + x}]"
+
+    def build(x, base):
+        if x & (x - 1) == 0 or (x, base) in built:
+            return
+        parent, low = x & (x - 1), x & -x
+        build(parent, base)
+        built.add((x, base))
+        stmts.append(f"{name(x, base)} = {name(parent, base)} ^ {name(low, base)};")
+
+    for lo, hi, idx in uses:
+        terms = []
+        if lo:
+            build(lo, 0)
+            terms.append(name(lo, 0))
+        if hi:
+            build(hi, 4)
+            terms.append(name(hi, 4))
+        stmts.append(f"acc[{idx}] ^= {' ^ '.join(terms)};")
+    n = len(stmts)
+    return [stmts[n * j // N_PARTS: n * (j + 1) // N_PARTS] for j in range(N_PARTS)]
+
+
 def emit_net(L, k, m, v, rows, mt, r0):
     L.append(f"template <> struct BsNet<{k}, {m}, {v}> {{")
     L.append(f"  static constexpr int K = {k}, M = {m}, kTotalM = {mt}, kRow0 = {r0};")
@@ -163,7 +206,63 @@ def emit_net(L, k, m, v, rows, mt, r0):
         L.extend("  " + ln for ln in body)
         L.append("    }")
     L.append("  }")
+    L.append(f"  static constexpr int kParts = {N_PARTS};")
+    L.append("  // the same network in kParts pieces (combinations created just before first use, kept in t[])")
+    L.append("  template <int C, int J> static __device__ __forceinline__ void part(const uint32_t (&p)[8], uint32_t (&acc)[8 * M], uint32_t (&t)[32]) {")
+    for c in range(k):
+        parts = emit_shard_parts([rows[r][c] for r in range(m)])
+        for j, st in enumerate(parts):
+            if st:
+                L.append(f"    if constexpr (C == {c} && J == {j}) {{ " + " ".join(st) + " }")
+    L.append("  }")
     L.append("};")
+
+
+def const_mul_statements(g):
+    """Statements of a[i] ^= plane i of (g * x): greedy common-pair elimination (Paar) over the 8x8 bit
+    matrix of the constant, then every row folded two signals per 3-input XOR."""
+    rows = [set(f"p[{j}]" for j in range(8) if (mk >> j) & 1) for mk in row_masks(g)]
+    stmts, ntmp = [], 0
+    while True:
+        best, cnt = None, 1
+        sigs = sorted(set().union(*rows))
+        for a in range(len(sigs)):
+            for b in range(a + 1, len(sigs)):
+                c = sum(1 for r in rows if sigs[a] in r and sigs[b] in r)
+                if c > cnt:
+                    best, cnt = (sigs[a], sigs[b]), c
+        if best is None:
+            break
+        # a shared pair pays when it saves LOP3s: rows with an odd number of signals lose nothing by keeping
+        # one signal unpaired, so only take pairs used by at least 3 rows (1 LOP3 to build, >= 1.5 saved)
+        if cnt < 3:
+            break
+        name = f"t{ntmp}"
+        ntmp += 1
+        stmts.append(f"const uint32_t {name} = {best[0]} ^ {best[1]};")
+        for r in rows:
+            if best[0] in r and best[1] in r:
+                r.discard(best[0])
+                r.discard(best[1])
+                r.add(name)
+    for i, r in enumerate(rows):
+        terms = sorted(r)
+        while terms:
+            take, terms = terms[:2], terms[2:]
+            stmts.append(f"a[{i}] ^= {' ^ '.join(take)};")
+    return stmts
+
+
+def emit_const_multipliers(L):
+    """BsMul<G>::mac(p, a): a[i] ^= plane i of (G * x) for every field constant G -- the networks of the
+    generic bit-sliced kernel (bitslice_gen.cu), which picks one per (input shard, output) at run time
+    through a 256-way switch on the coefficient (reconstruct with data-dependent decode rows, custom
+    matrices)."""
+    L.append("// ---- constant multipliers: a[i] ^= plane i of (G * x), x given as 8 bit-planes p[0..7]")
+    L.append("template <int G> struct BsMul;")
+    for g in range(1, 256):
+        L.append(f"template <> struct BsMul<{g}> {{ static __device__ __forceinline__ void mac(const uint32_t (&p)[8], uint32_t (&a)[8]) {{ "
+                 + " ".join(const_mul_statements(g)) + " } };")
 
 
 def pass_split(mt, width):
@@ -209,6 +308,7 @@ def main(out_path):
             for pi, (r0, m) in enumerate(pass_split(mt, width)):
                 emit_net(L, k, m, pass_id(mt, r0, plan), rows[r0:r0 + m], mt, r0)
                 passes.append(f"X({k}, {m}, {pass_id(mt, r0, plan)}, {mt}, {r0}, {pi}, {plan})")
+    emit_const_multipliers(L)
     L.append("}  // namespace cbe")
     L.append("// X(K, M): single-pass configurations;  X(K, M, V, MT, R0, PASS, PLAN): passes of the MT > 4 codes (plan 0: fused CRC, plan 1: plain/verify)")
     L.append("#define CUBEEC_BS_CONFIGS(X) " + " ".join(full))

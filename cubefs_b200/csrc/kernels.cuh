@@ -148,6 +148,70 @@ struct BsParams {
 };
 
 
+// ---- fused encode + CRC32, flat work split (bs_flat.cuh, bitslice_flat.cu) -----------------------------
+// Units (2 KiB of every shard of one stripe) are numbered stripe-major; warp g of the grid takes units
+// [g*U/GW, (g+1)*U/GW).  crc_part[((stripe * n_slots + slot) * max_parts + j)] = remainder of the j-th run that
+// touches the stripe (aligned to the end of its last unit there); crc_parts_finalize_kernel chains them.
+constexpr int kBsfFoldCopies = 8;
+#ifndef CUBEEC_BSF_THREADS
+#define CUBEEC_BSF_THREADS 384
+#endif
+constexpr int kBsfThreads = CUBEEC_BSF_THREADS;   // 12 warps x 168 registers: room for the interleaved schedule (bs_flat.cuh)
+constexpr int kBsfUnitBytes = 32 * kBsPiece;   // bytes of a shard per unit
+constexpr size_t kBsfSmemBytes = 65536 + kBsSliceImageBytes + 1024;
+struct BsfParams {
+  uint8_t* base;
+  size_t stripe_pitch, shard_pitch;
+  uint32_t shard_len, n_stripes;
+  uint32_t n_slots;
+  uint32_t units_per_shard;           // ceil(shard_len / kBsfUnitBytes)
+  uint64_t total_units;               // n_stripes * units_per_shard
+  uint32_t max_parts;
+  uint32_t poly;
+  uint32_t* crc_part;
+  uint8_t in_slot[24];
+  uint8_t out_slot[8];
+  const uint32_t* slice_image;        // global: 128 KiB lane-private slicing tables
+  const uint32_t* fold_tables;        // global: [4][256] register * x^(8*(unit - piece))
+  const uint32_t* klane;              // global: [32] x^(8 * piece * (31 - lane))
+};
+struct CrcPartsFinalizeParams {
+  const uint32_t* crc_part;           // [n_stripes][n_slots][max_parts]
+  uint32_t n_stripes, n_slots, max_parts;
+  uint32_t units_per_shard;
+  uint64_t total_units, total_warps;  // U and GW of the launch that produced the parts
+  uint32_t shard_len;
+  uint32_t first_slot, n_out;         // slots [first_slot, first_slot + n_out) are finalized (others untouched)
+  uint32_t poly;
+  uint32_t x_unit_pow[24];            // x^(8 * kBsfUnitBytes * 2^i)
+  uint32_t fix;                       // x^(-8 * (units_per_shard * kBsfUnitBytes - shard_len))
+  uint32_t init_term;                 // 0xFFFFFFFF * x^(8 * shard_len)
+  uint32_t* out;                      // [n_stripes][n_slots]
+};
+cudaError_t launch_crc_parts_finalize(const CrcPartsFinalizeParams& p, cudaStream_t stream);
+// does bitslice_flat.cu have RS(k, m) pass `pass` of plan 0 with this CRC mode (1 all shards, 2 outputs only)?
+bool bsf_supported(int k, int m, int pass, int crc_mode);
+cudaError_t launch_bsf(int k, int m, int pass, int crc_mode, const BsfParams& p, int grid, cudaStream_t st);
+// A/B measurement aid: RS(12,4) mode 1 with another CTA size (threads in {512, 448, 384, 320, 256})
+cudaError_t launch_bsf_variant(int threads, const BsfParams& p, int grid, cudaStream_t st);
+
+
+// ---- generic bit-sliced coding kernel (bitslice_gen.cu): run-time coefficients, flat work split -------
+constexpr int kBsgThreads = 512;
+struct BsgParams {
+  uint8_t* base;
+  size_t stripe_pitch, shard_pitch;
+  uint32_t shard_len, n_stripes;
+  uint32_t units_per_shard;           // bsg_units_per_shard(shard_len)
+  uint64_t total_units;               // n_stripes * units_per_shard
+  const Pattern* patterns;
+  const uint32_t* pattern_of_stripe;  // nullptr -> pattern 0 for every stripe
+  int32_t* mismatch;                  // compare mode: [n_stripes], set to 1 on any difference
+};
+uint32_t bsg_units_per_shard(size_t shard_len);
+// max_out: largest n_out of any pattern of the launch (1..4); mode 0 = store outputs, 1 = compare with stored
+cudaError_t launch_bsg(const BsgParams& p, int max_out, int mode, int grid, cudaStream_t st);
+
 // ---- bit-sliced syndrome reconstruct (bitslice.cu) ---------------------------------------------
 // The reference decodes from the first k present shards (RS/reedsolomon.go:1453-1465).  Data indices
 // precede parity indices, so that set is: every present data shard + the first e_d present parity

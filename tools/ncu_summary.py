@@ -16,6 +16,9 @@ print(f"# ncu summary of {rep.split('/')[-1]}")
 print("kernel:", get("Kernel Name")[0][:110])
 print("grid/block:", get("Grid Size")[0], "/", get("Block Size")[0], " registers/thread:", get("launch__registers_per_thread")[0])
 for key in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "lts__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum",
+            "l1tex__t_sector_hit_rate.pct", "smsp__inst_executed_per_warp.ratio", "launch__occupancy_limit_registers",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
             "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
             "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
