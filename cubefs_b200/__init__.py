@@ -11,4 +11,4 @@ package is the Python host-side binding used by tests and bench.py:
 There is no CPU compute path: importing works anywhere, calling needs a CUDA device.
 """
 from .engine import (CubeecError, RSEngine, crc32, crc32_blocks, dev_lrc_encode, device_count, force_kernel,  # noqa: F401
-                     init, kernel_launches, last_kernel, lib_path, load, lrc_encode_contig)
+                     init, kernel_launches, last_kernel, lib_path, load, lrc_encode_contig, set_coalescing)

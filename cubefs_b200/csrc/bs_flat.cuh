@@ -76,10 +76,12 @@ __host__ __device__ __forceinline__ uint64_t bsf_owner(uint64_t u, uint64_t U, u
 }
 
 // CRC: 1 = every shard, 2 = the M outputs only (later passes of an m > 4 code, LRC local stripes).
-template <int K, int M, int V, int CRC, int NT>
+// RD = number of 256-bit load buffers (RD - 1 shards in flight ahead of the one being coded).
+template <int K, int M, int V, int CRC, int NT, int RD = (NT <= 384 ? 4 : 3)>
 __global__ void __launch_bounds__(NT, 1) rs_bsf_kernel(const BsfParams p) {
   static_assert(CRC == 1 || CRC == 2, "fused-CRC kernel");
   static_assert(K >= 2 && K + M <= 32, "lane q publishes the remainder of shard q");
+  static_assert(RD >= 3 && K >= RD - 1, "load ring");
   using Net = BsNet<K, M, V>;
   constexpr int C0 = CRC == 2 ? K : 0;   // first checksummed shard (local index)
   constexpr int NW = NT / 32;
@@ -151,11 +153,11 @@ __global__ void __launch_bounds__(NT, 1) rs_bsf_kernel(const BsfParams p) {
   uint32_t crc_u[K + M];
 #pragma unroll
   for (int i = 0; i < K + M; i++) crc_u[i] = 0;
-  // three 256-bit buffers: shard c is coded from ring[c % 3] while shard c+1 is checksummed in ring[(c+1) % 3]
-  // and shard c+2 is in flight into ring[(c+2) % 3]
-  uint32_t ring[3][8];
+  // RD 256-bit buffers: shard c is coded from ring[c % RD] while shard c+1 is checksummed in ring[(c+1) % RD]
+  // and shards c+2 .. c+RD-1 are in flight
+  uint32_t ring[RD][8];
 #pragma unroll
-  for (int b = 0; b < 3; b++)
+  for (int b = 0; b < RD; b++)
 #pragma unroll
     for (int i = 0; i < 8; i++) ring[b][i] = 0;
 
@@ -178,8 +180,8 @@ __global__ void __launch_bounds__(NT, 1) rs_bsf_kernel(const BsfParams p) {
     return c;
   };
 
-  // ---- one 32-byte column of every shard.  ring[0] / ring[1] already hold (or are receiving) data shards
-  // 0 and 1 of this column; on return they hold shards 0 and 1 of column `nx` (if nx.live).
+  // ---- one 32-byte column of every shard.  ring[0 .. RD-2] already hold (or are receiving) data shards
+  // 0 .. RD-2 of this column; on return they hold those of column `nx` (if nx.live).
   auto column = [&](auto full_tag, const Col cc, const Col nx, const bool nx_valid) {
     constexpr bool FULL = decltype(full_tag)::value;
     uint32_t msk[8];
@@ -215,15 +217,15 @@ __global__ void __launch_bounds__(NT, 1) rs_bsf_kernel(const BsfParams p) {
     }
     StaticFor<0, K>::run([&](auto cconst) {
       constexpr int c = decltype(cconst)::value;
-      // load two shards ahead; past the last data shard: shards 0 and 1 of the next column
-      if constexpr (c + 2 < K) {
-        if (FULL || cc.live) ldg256(src + (size_t)p.in_slot[c + 2] * p.shard_pitch, ring[(c + 2) % 3]);
+      // load RD-1 shards ahead; past the last data shard: shards 0 .. RD-2 of the next column
+      if constexpr (c + RD - 1 < K) {
+        if (FULL || cc.live) ldg256(src + (size_t)p.in_slot[c + RD - 1] * p.shard_pitch, ring[(c + RD - 1) % RD]);
       } else {
-        if (nlive) ldg256(nsrc + (size_t)p.in_slot[c + 2 - K] * p.shard_pitch, ring[(c + 2) % 3]);
+        if (nlive) ldg256(nsrc + (size_t)p.in_slot[c + RD - 1 - K] * p.shard_pitch, ring[(c + RD - 1) % RD]);
       }
-      uint32_t (&w)[8] = ring[c % 3];
+      uint32_t (&w)[8] = ring[c % RD];
       if constexpr (c + 1 < K) {
-        uint32_t (&wn)[8] = ring[(c + 1) % 3];
+        uint32_t (&wn)[8] = ring[(c + 1) % RD];
         mask_buf(wn);
         uint32_t u = CRC == 1 ? crc_u[c + 1] : 0u;
         StaticFor<0, 8>::run([&](auto jc) {
@@ -264,14 +266,17 @@ __global__ void __launch_bounds__(NT, 1) rs_bsf_kernel(const BsfParams p) {
       });
       if constexpr (r > 0) crc_u[K + r - 1] = u;
     });
-    // (ring[(K) % 3], ring[(K+1) % 3] now hold the next column's shards 0 and 1)
-    if constexpr (K % 3 != 0) {
+    // (ring[(K + j) % RD] now holds the next column's shard j, j < RD - 1: move them to ring[j])
+    if constexpr (K % RD != 0) {
+      uint32_t tmp[RD - 1][8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const uint32_t a = ring[K % 3][i], b = ring[(K + 1) % 3][i];
-        ring[0][i] = a;
-        ring[1][i] = b;
-      }
+      for (int j = 0; j < RD - 1; j++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) tmp[j][i] = ring[(K + j) % RD][i];
+#pragma unroll
+      for (int j = 0; j < RD - 1; j++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) ring[j][i] = tmp[j][i];
     }
   };
 
@@ -297,8 +302,8 @@ __global__ void __launch_bounds__(NT, 1) rs_bsf_kernel(const BsfParams p) {
     {
       const Col c0 = locate(s, t, 0);
       if (c0.live) {
-        ldg256(c0.sbase + c0.col + (size_t)p.in_slot[0] * p.shard_pitch, ring[0]);
-        ldg256(c0.sbase + c0.col + (size_t)p.in_slot[1] * p.shard_pitch, ring[1]);
+#pragma unroll
+        for (int j = 0; j < RD - 1; j++) ldg256(c0.sbase + c0.col + (size_t)p.in_slot[j] * p.shard_pitch, ring[j]);
       }
     }
     for (uint64_t u = u_lo; u < u_hi; u++) {

@@ -6,6 +6,7 @@
 // the CUDA kernels in kernels.cu / bitslice.cu; without a device the calls fail.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -201,14 +202,18 @@ int ensure_init() {
     return CUBEEC_ERR_NO_DEVICE;   // not cached: a later call may find a device
   }
   if (g.devices.empty()) g.devices.push_back(0);
+  // contexts are built aside and committed only when every device came up (a failed attempt leaves no
+  // half-initialised state behind; its device tables are released with the process)
+  std::vector<std::unique_ptr<DevCtx>> fresh;
   for (int d : g.devices) {
     if (d < 0 || d >= n) return CUBEEC_ERR_INVALID_ARG;
     auto c = std::make_unique<DevCtx>();
     c->device = d;
     int rc = setup_device(*c);
     if (rc) return rc;
-    g.ctx.push_back(std::move(c));
+    fresh.push_back(std::move(c));
   }
+  g.ctx = std::move(fresh);
   g.ready = true;
   g.init_rc = CUBEEC_OK;
   return CUBEEC_OK;
@@ -239,7 +244,14 @@ struct LaneLease {
         lane = new Lane();
         cudaSetDevice(c->device);
         cudaError_t e = cudaStreamCreateWithFlags(&lane->stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+        if (e != cudaSuccess) {
+          delete lane;
+          lane = nullptr;   // the destructor must not pool a lane without a stream
+          lk.lock();
+          c->lanes_created--;
+          c->cv.notify_one();
+          return cuda_fail(e, "cudaStreamCreate");
+        }
         break;
       }
       c->cv.wait(lk);
@@ -651,6 +663,9 @@ int bs_run(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t sh
   return CUBEEC_OK;
 }
 
+int dev_crc32_impl(DevCtx& c, cudaStream_t st, const uint8_t* d_base, size_t len, size_t pitch, size_t n_buffers,
+                   size_t block, int crc_poly, uint32_t* d_whole, uint32_t* d_blocks);
+
 // ---- flat work split of the fused encode + CRC kernel (bs_flat.cuh) ----------------------------------
 struct FlatGeometry {
   uint32_t units_per_shard = 0;
@@ -773,6 +788,18 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
                     size_t shard_pitch, size_t stripe_pitch, size_t n_stripes, uint32_t* d_crc_out, int crc_poly,
                     int mode, int32_t* d_mismatch, uint32_t* d_part) {
   if (h->m == 0 && !d_crc_out) return CUBEEC_OK;
+  if (h->m == 0) {
+    // reedsolomon.New(N, 0) (the Replica code modes): nothing to code, the checksums are plain buffer CRCs
+    if (mode != 0) return CUBEEC_OK;
+    if (stripe_pitch == (size_t)h->k * shard_pitch)
+      return dev_crc32_impl(c, stream, d_base, shard_len, shard_pitch, n_stripes * (size_t)h->k, 0, crc_poly, d_crc_out, nullptr);
+    for (size_t s = 0; s < n_stripes; s++) {
+      int rc = dev_crc32_impl(c, stream, d_base + s * stripe_pitch, shard_len, shard_pitch, (size_t)h->k, 0, crc_poly,
+                              d_crc_out + s * (size_t)h->k, nullptr);
+      if (rc) return rc;
+    }
+    return CUBEEC_OK;
+  }
   const int n = h->k + h->m;
   const size_t ci = ctx_index(&c);
   const bool want_crc = mode == 0 && d_crc_out;
@@ -957,11 +984,19 @@ extern "C" int cubeec_decode_matrix(const cubeec_t* h, const uint8_t* present, i
 // ------------------------------------------------------------------------------------------
 // device-resident API
 // ------------------------------------------------------------------------------------------
-static int check_dev_layout(const void* d_base, size_t shard_len, size_t shard_pitch, size_t stripe_pitch) {
+static int check_dev_layout(const void* d_base, size_t shard_len, size_t shard_pitch, size_t stripe_pitch, int n_slots = 0,
+                            size_t n_stripes = 0) {
   if (!d_base || shard_len == 0) return CUBEEC_ERR_INVALID_ARG;
   if (((uintptr_t)d_base & 15) || (shard_pitch & 15) || (stripe_pitch & 15) || shard_pitch < shard_len)
     return CUBEEC_ERR_INVALID_ARG;
   if (shard_len > 0xFFFFFFF0ull) return CUBEEC_ERR_UNSUPPORTED;
+  // stripes must not overlap, and the kernels count stripes / work items in 32 bits
+  if (n_slots > 0 && stripe_pitch < (size_t)n_slots * shard_pitch) return CUBEEC_ERR_INVALID_ARG;
+  if (n_stripes > 0) {
+    const uint64_t units = (shard_len + 1023) / 1024;   // upper bound of work items per stripe over all kernels
+    if (n_stripes >= (1ull << 31) || n_stripes * (uint64_t)std::max(n_slots, 1) >= (1ull << 32) || n_stripes * units >= (1ull << 40))
+      return CUBEEC_ERR_UNSUPPORTED;
+  }
   return CUBEEC_OK;
 }
 
@@ -971,7 +1006,7 @@ extern "C" int cubeec_dev_encode(cubeec_t* h, int device, void* d_base, size_t s
   if (!h) return CUBEEC_ERR_INVALID_ARG;
   int rc = ensure_init();
   if (rc) return rc;
-  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch))) return rc;
+  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch, h->k + h->m, n_stripes))) return rc;
   if (n_stripes == 0) return CUBEEC_OK;
   DevCtx* c = ctx_for_device(device);
   if (!c) return CUBEEC_ERR_INVALID_ARG;
@@ -1084,7 +1119,7 @@ extern "C" int cubeec_dev_lrc_encode(cubeec_t* global, cubeec_t* local, int az_c
   int rc = lrc_layout(global, local, az_count, &y);
   if (rc) return rc;
   if ((rc = ensure_init())) return rc;
-  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch))) return rc;
+  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch, y.N + y.M + y.L, n_stripes))) return rc;
   if (n_stripes == 0) return CUBEEC_OK;
   DevCtx* c = ctx_for_device(device);
   if (!c) return CUBEEC_ERR_INVALID_ARG;
@@ -1111,7 +1146,7 @@ extern "C" int cubeec_dev_verify(cubeec_t* h, int device, const void* d_base, si
   if (!h || !d_ok) return CUBEEC_ERR_INVALID_ARG;
   int rc = ensure_init();
   if (rc) return rc;
-  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch))) return rc;
+  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch, h->k + h->m, n_stripes))) return rc;
   if (n_stripes == 0) return CUBEEC_OK;
   DevCtx* c = ctx_for_device(device);
   if (!c) return CUBEEC_ERR_INVALID_ARG;
@@ -1139,7 +1174,7 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
   if (!h || !present) return CUBEEC_ERR_INVALID_ARG;
   int rc = ensure_init();
   if (rc) return rc;
-  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch))) return rc;
+  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch, h->k + h->m, n_stripes))) return rc;
   if (n_stripes == 0) return CUBEEC_OK;
   DevCtx* c = ctx_for_device(device);
   if (!c) return CUBEEC_ERR_INVALID_ARG;
@@ -1308,6 +1343,245 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
 }
 
 // ------------------------------------------------------------------------------------------
+// Coalescing submit queue for the single-stripe host calls.
+//
+// How access calls the codec (blobstore/common/ec/encoder.go:114-131): ONE stripe per Encode call, at most 4
+// blobs of a request in flight (access/stream/stream_put.go:105-110), up to defaultEncoderConcurrency = 1000
+// goroutines in the call at once (access/stream/config_defaulter.go:24).  A cgo call pins an OS thread for its
+// duration, so the natural shape is: the caller threads block, the library forms the batches.
+//
+//   caller thread   claim a slot of the OPEN batch of its (handle, shard size, checksum) key  -> copy its k data
+//                   shards from pageable memory into the slot of the batch's PINNED staging buffer (the copies of
+//                   all callers run in parallel, on the callers' own cores) -> wait for the batch -> copy its m
+//                   parity shards (+ CRCs) out of the pinned buffer.
+//   worker threads  (kCoWorkers per device, one lane/stream each) take a batch once it is full or its deadline
+//                   (first claim + delay) has passed and every claimed slot is filled: ONE 2-D H2D copy, the same
+//                   device encode as cubeec_dev_encode (fused CRC), ONE 2-D D2H copy of the parity columns.
+//                   Three workers keep the H2D of one batch, the kernels of the next and the D2H of a third in flight.
+//
+// cubeec_set_coalescing(max_batch, delay_us): max_batch <= 1 switches the queue off (every call then does its own
+// H2D / kernel / D2H round trip, the round-1 behaviour).
+// ------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kCoWorkers = 3;
+constexpr size_t kCoBatchBytes = 160u << 20;   // pinned staging of one batch
+
+struct CoBatch {
+  cubeec* h = nullptr;
+  size_t S = 0, P = 0;
+  int n = 0, poly = 0;
+  bool want_crc = false;
+  int cap = 0, claimed = 0, filled = 0, left = 0;   // left: callers that still have to copy their results out
+  enum { OPEN, CLOSED, RUNNING, DONE } state = OPEN;
+  std::chrono::steady_clock::time_point deadline;
+  uint8_t* h_buf = nullptr;     // pinned: [cap][n][P]
+  size_t h_cap = 0;
+  uint32_t* h_crc = nullptr;    // pinned: [cap][n]
+  size_t crc_cap = 0;
+  int rc = CUBEEC_OK;
+  std::string err;
+  std::condition_variable done_cv;
+};
+
+struct CoQueue {
+  std::mutex mu;
+  std::condition_variable work_cv;
+  std::vector<CoBatch*> open;       // batches that still accept claims
+  std::vector<CoBatch*> pending;    // closed or open-with-deadline batches waiting for a worker (FIFO)
+  std::vector<CoBatch*> pool;       // idle batch objects (their pinned buffers are kept)
+  std::vector<std::thread> workers;
+  bool started = false, stop = false;
+  DevCtx* ctx = nullptr;
+};
+
+std::atomic<int> g_co_max_batch{32};
+std::atomic<int> g_co_delay_us{100};
+CoQueue g_co;   // device 0 of the engine (the single-stripe host calls always use the first configured device)
+
+int co_run_batch(CoBatch& b, DevCtx& c, Lane& l) {
+  const size_t dstripe = b.P * b.n;
+  const int k = b.h->k, m = b.h->m;
+  const size_t part_bytes = b.want_crc ? round_up(crc_part_bytes(c, b.S, (size_t)b.claimed, b.n), 256) : 0;
+  int rc = lane_reserve(l, dstripe * b.claimed, part_bytes + (size_t)b.claimed * b.n * 4 + 256);
+  if (rc) return rc;
+  CU(cudaSetDevice(c.device));
+  // data columns of every slot in one 2-D copy (row = one slot: k*P of its n*P bytes)
+  CU(cudaMemcpy2DAsync(l.d_buf, dstripe, b.h_buf, dstripe, (size_t)k * b.P, (size_t)b.claimed, cudaMemcpyHostToDevice, l.stream));
+  uint32_t* d_part = b.want_crc ? reinterpret_cast<uint32_t*>(l.d_aux) : nullptr;
+  uint32_t* d_crc = b.want_crc ? reinterpret_cast<uint32_t*>(l.d_aux + part_bytes) : nullptr;
+  rc = dev_encode_impl(b.h, c, l.stream, l.d_buf, b.S, b.P, dstripe, (size_t)b.claimed, d_crc, b.poly, 0, nullptr, d_part);
+  if (rc) return rc;
+  if (m > 0)
+    CU(cudaMemcpy2DAsync(b.h_buf + (size_t)k * b.P, dstripe, l.d_buf + (size_t)k * b.P, dstripe, (size_t)m * b.P, (size_t)b.claimed,
+                         cudaMemcpyDeviceToHost, l.stream));
+  if (b.want_crc) CU(cudaMemcpyAsync(b.h_crc, d_crc, (size_t)b.claimed * b.n * 4, cudaMemcpyDeviceToHost, l.stream));
+  CU(cudaStreamSynchronize(l.stream));
+  return CUBEEC_OK;
+}
+
+void co_worker() {
+  CoQueue& q = g_co;
+  LaneLease lease;
+  const int lrc = lease.acquire(q.ctx);
+  std::unique_lock<std::mutex> lk(q.mu);
+  for (;;) {
+    // first batch that can start: all claimed slots filled and (closed or past its deadline)
+    CoBatch* b = nullptr;
+    auto next_deadline = std::chrono::steady_clock::time_point::max();
+    const auto now = std::chrono::steady_clock::now();
+    for (size_t i = 0; i < q.pending.size(); i++) {
+      CoBatch* x = q.pending[i];
+      if (x->state == CoBatch::OPEN && now >= x->deadline) {
+        x->state = CoBatch::CLOSED;   // no more claims
+        q.open.erase(std::remove(q.open.begin(), q.open.end(), x), q.open.end());
+      }
+      if (x->state == CoBatch::CLOSED && x->filled == x->claimed) {
+        b = x;
+        q.pending.erase(q.pending.begin() + (long)i);
+        break;
+      }
+      if (x->state == CoBatch::OPEN) next_deadline = std::min(next_deadline, x->deadline);
+    }
+    if (!b) {
+      if (q.stop) return;
+      if (next_deadline == std::chrono::steady_clock::time_point::max()) q.work_cv.wait(lk);
+      else q.work_cv.wait_until(lk, next_deadline);
+      continue;
+    }
+    b->state = CoBatch::RUNNING;
+    lk.unlock();
+    int rc = lrc ? lrc : co_run_batch(*b, *q.ctx, *lease.lane);
+    std::string err = rc ? t_last_error : std::string();
+    lk.lock();
+    b->rc = rc;
+    b->err = err;
+    b->state = CoBatch::DONE;
+    b->done_cv.notify_all();
+  }
+}
+
+void co_start_locked(CoQueue& q) {
+  if (q.started) return;
+  q.started = true;
+  q.ctx = g.ctx[0].get();
+  for (int i = 0; i < kCoWorkers; i++) q.workers.emplace_back(co_worker);
+  // the workers are joined at process exit: a detached worker would race with CUDA's own teardown
+  std::atexit([] {
+    CoQueue& qq = g_co;
+    {
+      std::lock_guard<std::mutex> lk(qq.mu);
+      qq.stop = true;
+      qq.work_cv.notify_all();
+    }
+    for (auto& t : qq.workers)
+      if (t.joinable()) t.join();
+  });
+}
+
+// cubeec_encode through the queue.  Returns -1 when the call is not eligible (queue off, m == 0, ...).
+int co_encode(cubeec* h, uint8_t* const* shards, size_t S, int n, uint32_t* crc_out, int crc_poly) {
+  const int max_batch = g_co_max_batch.load();
+  if (max_batch <= 1 || h->m == 0) return -1;
+  const size_t P = round_up(S, kAlign);
+  const size_t dstripe = P * n;
+  int cap = (int)std::min<size_t>((size_t)max_batch, std::max<size_t>(1, kCoBatchBytes / dstripe));
+  if (cap <= 1) return -1;   // stripes this large are a batch by themselves
+  CoQueue& q = g_co;
+  CoBatch* b = nullptr;
+  int idx = 0;
+  {
+    std::unique_lock<std::mutex> lk(q.mu);
+    co_start_locked(q);
+    for (CoBatch* x : q.open)
+      if (x->h == h && x->S == S && x->poly == crc_poly && x->want_crc == (crc_out != nullptr) && x->state == CoBatch::OPEN &&
+          x->claimed < x->cap) {
+        b = x;
+        break;
+      }
+    if (!b) {
+      if (!q.pool.empty()) {
+        b = q.pool.back();
+        q.pool.pop_back();
+      } else {
+        b = new CoBatch();
+      }
+      b->h = h;
+      b->S = S;
+      b->P = P;
+      b->n = n;
+      b->poly = crc_poly;
+      b->want_crc = crc_out != nullptr;
+      b->cap = cap;
+      b->claimed = b->filled = b->left = 0;
+      b->state = CoBatch::OPEN;
+      b->rc = CUBEEC_OK;
+      b->deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(std::max(0, g_co_delay_us.load()));
+      const size_t need = dstripe * (size_t)cap, need_crc = (size_t)cap * n * 4;
+      if (need > b->h_cap || need_crc > b->crc_cap) {
+        lk.unlock();   // pinned allocation is slow: not under the queue lock
+        if (b->h_buf) cudaFreeHost(b->h_buf);
+        if (b->h_crc) cudaFreeHost(b->h_crc);
+        b->h_buf = nullptr;
+        b->h_crc = nullptr;
+        b->h_cap = b->crc_cap = 0;
+        cudaSetDevice(q.ctx->device);
+        cudaError_t e = cudaMallocHost(&b->h_buf, need);
+        if (e == cudaSuccess) e = cudaMallocHost(&b->h_crc, need_crc);
+        lk.lock();
+        if (e != cudaSuccess) {
+          if (b->h_buf) cudaFreeHost(b->h_buf);
+          b->h_buf = nullptr;
+          q.pool.push_back(b);
+          return cuda_fail(e, "cudaMallocHost(coalescing batch)");
+        }
+        b->h_cap = need;
+        b->crc_cap = need_crc;
+      }
+      q.open.push_back(b);
+      q.pending.push_back(b);
+    }
+    idx = b->claimed++;
+    b->left++;
+    if (b->claimed == b->cap) {
+      b->state = CoBatch::CLOSED;
+      q.open.erase(std::remove(q.open.begin(), q.open.end(), b), q.open.end());
+    }
+    if (idx == 0) q.work_cv.notify_one();   // a worker has to watch the new deadline
+  }
+  // fill the slot from the caller's (pageable) memory, in the caller's thread
+  uint8_t* slot = b->h_buf + (size_t)idx * dstripe;
+  for (int i = 0; i < h->k; i++) std::memcpy(slot + (size_t)i * P, shards[i], S);
+  int rc;
+  {
+    std::unique_lock<std::mutex> lk(q.mu);
+    b->filled++;
+    if (b->filled == b->claimed) q.work_cv.notify_all();
+    b->done_cv.wait(lk, [&] { return b->state == CoBatch::DONE; });
+    rc = b->rc;
+    if (rc) t_last_error = b->err;
+  }
+  if (rc == CUBEEC_OK) {
+    for (int i = h->k; i < n; i++) std::memcpy(shards[i], slot + (size_t)i * P, S);
+    if (crc_out) std::memcpy(crc_out, b->h_crc + (size_t)idx * n, (size_t)n * 4);
+  }
+  {
+    std::lock_guard<std::mutex> lk(q.mu);
+    if (--b->left == 0) q.pool.push_back(b);   // last caller out recycles the batch (pinned buffers stay allocated)
+  }
+  return rc;
+}
+
+}  // namespace
+
+extern "C" int cubeec_set_coalescing(int max_batch, int delay_us) {
+  if (max_batch < 0 || delay_us < 0) return CUBEEC_ERR_INVALID_ARG;
+  g_co_max_batch.store(max_batch);
+  g_co_delay_us.store(delay_us);
+  return CUBEEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // single stripe, host scatter pointers
 // ------------------------------------------------------------------------------------------
 extern "C" int cubeec_encode(cubeec_t* h, uint8_t* const* shards, const size_t* lens, int n, uint32_t* crc_out,
@@ -1318,6 +1592,8 @@ extern "C" int cubeec_encode(cubeec_t* h, uint8_t* const* shards, const size_t* 
   int rc = check_shards(lens, n, false, &S);
   if (rc) return rc;
   if ((rc = ensure_init())) return rc;
+  rc = co_encode(h, shards, S, n, crc_out, crc_poly);   // coalescing queue (-1: not eligible, direct path below)
+  if (rc >= 0) return rc;
   DevCtx* c = g.ctx[0].get();
   LaneLease lease;
   if ((rc = lease.acquire(c))) return rc;
@@ -1368,9 +1644,11 @@ namespace {
 // Does not synchronize unless crc_out is given.  Small host->device control data (patterns,
 // enable flags) is copied from pageable memory, which the runtime stages before returning, so a
 // lane can be reused for the next stripe without a host-side wait.
+// crc_async (pinned, n words): batched form of crc_out -- the checksums of the regenerated shards are copied there
+// without a host-side wait (entries of shards that were not regenerated are undefined).
 int reconstruct_issue(cubeec* h, DevCtx& c, Lane& l, uint8_t* const* shards, const uint8_t* present, size_t S,
                       bool data_only, uint8_t* filled, uint32_t* crc_out, int crc_poly, bool* did_work,
-                      int32_t* verify_flag_host) {
+                      int32_t* verify_flag_host, uint32_t* crc_async = nullptr) {
   const int k = h->k, n = h->k + h->m;
   *did_work = false;
   int number_present = 0, data_present = 0;
@@ -1409,7 +1687,8 @@ int reconstruct_issue(cubeec* h, DevCtx& c, Lane& l, uint8_t* const* shards, con
   int32_t* d_flag = reinterpret_cast<int32_t*>(l.d_aux + o_flag);
   uint32_t* d_crc = reinterpret_cast<uint32_t*>(l.d_aux + o_crc);
   uint8_t* d_enable = l.d_aux + o_en;
-  uint32_t* d_part = crc_out ? reinterpret_cast<uint32_t*>(l.d_aux + o_part) : nullptr;
+  const bool want_crc = crc_out || crc_async;
+  uint32_t* d_part = want_crc ? reinterpret_cast<uint32_t*>(l.d_aux + o_part) : nullptr;
   if (!passes.empty()) {
     CU(cudaMemcpyAsync(d_pat, passes.data(), sizeof(Pattern) * passes.size(), cudaMemcpyHostToDevice, l.stream));
     std::vector<const Pattern*> pp;
@@ -1430,10 +1709,13 @@ int reconstruct_issue(cubeec* h, DevCtx& c, Lane& l, uint8_t* const* shards, con
         if (filled) filled[slot] = 1;
         CU(cudaMemcpyAsync(shards[slot], l.d_buf + slot * P, S, cudaMemcpyDeviceToHost, l.stream));
       }
-    if (crc_out) {
+    if (want_crc) {
       CU(cudaMemcpyAsync(d_enable, enable.data(), (size_t)n, cudaMemcpyHostToDevice, l.stream));
       rc = finalize_crc(c, l.stream, d_part, 1, n, S, gm, crc_poly, d_enable, d_crc);
       if (rc) return rc;
+    }
+    if (crc_async) CU(cudaMemcpyAsync(crc_async, d_crc, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
+    if (crc_out) {
       std::vector<uint32_t> h_crc(n);
       CU(cudaMemcpyAsync(h_crc.data(), d_crc, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
       CU(cudaStreamSynchronize(l.stream));
@@ -1443,7 +1725,15 @@ int reconstruct_issue(cubeec* h, DevCtx& c, Lane& l, uint8_t* const* shards, con
     *did_work = true;
   }
   if (verify_flag_host) {
-    // the repair loop's Verify right after Reconstruct (worker_slice_recover.go:871)
+    // the repair loop's Verify right after Reconstruct (worker_slice_recover.go:871).  Verify needs every shard:
+    // with data_only a missing parity shard stays missing (reedSolomon.Verify would fail with ErrShardSize on the
+    // empty shard, RS/reedsolomon.go:770-776)
+    if (data_only)
+      for (int i = k; i < n; i++)
+        if (!present[i]) {
+          cudaStreamSynchronize(l.stream);
+          return CUBEEC_ERR_SHARD_SIZE;
+        }
     CU(cudaMemsetAsync(d_flag, 0, sizeof(int32_t), l.stream));
     rc = dev_encode_impl(h, c, l.stream, l.d_buf, S, P, P * n, 1, nullptr, 0, 1, d_flag, nullptr);
     if (rc) return rc;
@@ -1471,13 +1761,23 @@ extern "C" int cubeec_reconstruct(cubeec_t* h, uint8_t* const* shards, const siz
   bool did = false;
   rc = reconstruct_issue(h, *c, *lease.lane, shards, present.data(), S, data_only != 0, filled, crc_out, crc_poly, &did,
                          nullptr);
-  if (rc) return rc;
+  if (rc) {
+    cudaStreamSynchronize(lease.lane->stream);   // copies from / to the caller's buffers may already be queued
+    return rc;
+  }
   if (did) CU(cudaStreamSynchronize(lease.lane->stream));
   return CUBEEC_OK;
 }
 
+extern "C" int cubeec_reconstruct_batch_crc(cubeec_t* h, const cubeec_stripe_t* stripes, size_t n_stripes, int data_only,
+                                            int* verify_ok, uint32_t* crc_out, int crc_poly);
 extern "C" int cubeec_reconstruct_batch(cubeec_t* h, const cubeec_stripe_t* stripes, size_t n_stripes, int data_only,
                                         int* verify_ok) {
+  return cubeec_reconstruct_batch_crc(h, stripes, n_stripes, data_only, verify_ok, nullptr, 0);
+}
+
+extern "C" int cubeec_reconstruct_batch_crc(cubeec_t* h, const cubeec_stripe_t* stripes, size_t n_stripes, int data_only,
+                                            int* verify_ok, uint32_t* crc_out, int crc_poly) {
   if (!h || (!stripes && n_stripes)) return CUBEEC_ERR_INVALID_ARG;
   int rc = ensure_init();
   if (rc) return rc;
@@ -1500,6 +1800,8 @@ extern "C" int cubeec_reconstruct_batch(cubeec_t* h, const cubeec_stripe_t* stri
     CU(cudaMallocHost(&h_flags, sizeof(int32_t) * std::max<size_t>(n_stripes, 1)));
     for (size_t s = 0; s < n_stripes; s++) h_flags[s] = 0;
   }
+  uint32_t* h_crc = nullptr;   // pinned [n_stripes][n]: checksums travel back asynchronously
+  if (crc_out) CU(cudaMallocHost(&h_crc, sizeof(uint32_t) * std::max<size_t>(n_stripes * (size_t)n, 1)));
   int result = CUBEEC_OK;
   for (size_t s = 0; s < n_stripes && result == CUBEEC_OK; s++) {
     LaneLease& ls = *leases[s % leases.size()];
@@ -1507,9 +1809,8 @@ extern "C" int cubeec_reconstruct_batch(cubeec_t* h, const cubeec_stripe_t* stri
     const cubeec_stripe_t& sp = stripes[s];
     if (!sp.shards || !sp.present || sp.shard_len == 0) { result = CUBEEC_ERR_INVALID_ARG; break; }
     bool did = false;
-    (void)n;
     result = reconstruct_issue(h, *ls.c, *ls.lane, sp.shards, sp.present, sp.shard_len, data_only != 0, nullptr, nullptr,
-                               0, &did, verify_ok ? &h_flags[s] : nullptr);
+                               crc_poly, &did, verify_ok ? &h_flags[s] : nullptr, crc_out ? h_crc + s * (size_t)n : nullptr);
   }
   for (auto& ls : leases) {
     cudaSetDevice(ls->c->device);
@@ -1519,6 +1820,14 @@ extern "C" int cubeec_reconstruct_batch(cubeec_t* h, const cubeec_stripe_t* stri
   if (verify_ok) {
     for (size_t s = 0; s < n_stripes; s++) verify_ok[s] = h_flags[s] ? 0 : 1;
     cudaFreeHost(h_flags);
+  }
+  if (crc_out) {
+    // only the shards this call regenerated carry a checksum: missing, and (data_only) not a parity shard
+    if (result == CUBEEC_OK)
+      for (size_t s = 0; s < n_stripes; s++)
+        for (int i = 0; i < n; i++)
+          if (!stripes[s].present[i] && !(data_only && i >= h->k)) crc_out[s * (size_t)n + i] = h_crc[s * (size_t)n + i];
+    cudaFreeHost(h_crc);
   }
   return result;
 }
@@ -1755,6 +2064,223 @@ extern "C" int cubeec_crc32_blocks(const uint8_t* p, size_t n, size_t block_payl
   if (rc) return rc;
   if (per_block && units) CU(cudaMemcpyAsync(per_block, d_blocks, units * 4, cudaMemcpyDeviceToHost, l.stream));
   if (whole) CU(cudaMemcpyAsync(whole, d_whole, 4, cudaMemcpyDeviceToHost, l.stream));
+  CU(cudaStreamSynchronize(l.stream));
+  return CUBEEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// crc32block framing on the device: the blobnode shard image body, the rpc body
+// (rpc.WithCrcEncode, BS/common/rpc/client.go:54-65 -> crc32block.NewBodyEncoder, request_body.go:81-130) and the
+// verification that datainspect / the block decoder do on every read (BS/blobnode/datainspect.go:246-283,
+// BS/common/crc32block/decode.go:84-107).
+// ------------------------------------------------------------------------------------------
+namespace {
+bool crc32block_valid_len(size_t block_len) { return block_len > 0 && block_len % 4096 == 0 && block_len <= (1u << 30); }
+
+int dev_crc_units(DevCtx& c, cudaStream_t st, const uint8_t* d_base, size_t pitch, size_t n_buffers, size_t len, size_t block,
+                  size_t stride, size_t offset, size_t units, int crc_poly, uint32_t* d_out) {
+  CrcRangeParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.base = d_base;
+  p.pitch = pitch;
+  p.n_buffers = (uint32_t)n_buffers;
+  p.len = (uint32_t)len;
+  p.block = (uint32_t)block;
+  p.units_per_buffer = (uint32_t)units;
+  p.crc = c.d_crc[crc_poly ? 1 : 0];
+  p.out = d_out;
+  p.stride = (uint32_t)stride;
+  p.offset = (uint32_t)offset;
+  const uint64_t total = (uint64_t)n_buffers * units;
+  CU(launch_crc_ranges(p, (int)std::min<uint64_t>(total, (uint64_t)c.sm_count * 4), st));
+  g_launches++;
+  t_last_kernel = "crc_range_kernel";
+  return CUBEEC_OK;
+}
+
+int dev_crc32block_encode_impl(DevCtx& c, cudaStream_t st, const uint8_t* d_src, size_t len, size_t src_pitch, size_t n_buffers,
+                               size_t block_len, uint8_t* d_dst, size_t dst_pitch, int crc_poly) {
+  const size_t payload = block_len - 4, blocks = (len + payload - 1) / payload;
+  AsyncScratch scratch(st);
+  CU(scratch.alloc(n_buffers * blocks * 4));
+  uint32_t* d_crcs = static_cast<uint32_t*>(scratch.ptr);
+  int rc = dev_crc_units(c, st, d_src, src_pitch, n_buffers, len, payload, payload, 0, blocks, crc_poly, d_crcs);
+  if (rc) return rc;
+  Crc32BlockParams fp;
+  std::memset(&fp, 0, sizeof(fp));
+  fp.plain = d_src;
+  fp.framed = d_dst;
+  fp.plain_pitch = src_pitch;
+  fp.framed_pitch = dst_pitch;
+  fp.plain_len = len;
+  fp.n_buffers = (uint32_t)n_buffers;
+  fp.n_blocks = (uint32_t)blocks;
+  fp.block_len = (uint32_t)block_len;
+  fp.mode = 0;
+  fp.crcs = d_crcs;
+  CU(launch_crc32block_frame(fp, c.sm_count * 8, st));
+  g_launches++;
+  t_last_kernel = "crc32block_frame_kernel";
+  return CUBEEC_OK;
+}
+
+int dev_crc32block_decode_impl(DevCtx& c, cudaStream_t st, const uint8_t* d_framed, size_t framed_len, size_t src_pitch,
+                               size_t n_buffers, size_t block_len, uint8_t* d_dst, size_t dst_pitch, int64_t* d_first_bad,
+                               uint8_t* d_block_ok, int crc_poly) {
+  const size_t blocks = (framed_len + block_len - 1) / block_len;
+  const size_t plain_len = framed_len - 4 * blocks;
+  AsyncScratch scratch(st);
+  CU(scratch.alloc(n_buffers * blocks * 4));
+  uint32_t* d_crcs = static_cast<uint32_t*>(scratch.ptr);
+  int rc = dev_crc_units(c, st, d_framed, src_pitch, n_buffers, framed_len, block_len - 4, block_len, 4, blocks, crc_poly, d_crcs);
+  if (rc) return rc;
+  Crc32BlockParams fp;
+  std::memset(&fp, 0, sizeof(fp));
+  fp.plain = d_dst;
+  fp.framed = d_framed;
+  fp.plain_pitch = dst_pitch;
+  fp.framed_pitch = src_pitch;
+  fp.plain_len = plain_len;
+  fp.n_buffers = (uint32_t)n_buffers;
+  fp.n_blocks = (uint32_t)blocks;
+  fp.block_len = (uint32_t)block_len;
+  fp.crcs = d_crcs;
+  fp.block_ok = d_block_ok;
+  fp.first_bad = d_first_bad;
+  if (d_first_bad) CU(cudaMemsetAsync(d_first_bad, 0xFF, n_buffers * sizeof(int64_t), st));   // -1 = every block good
+  if (d_first_bad || d_block_ok) {
+    CU(launch_crc32block_check(fp, st));
+    g_launches++;
+    t_last_kernel = "crc32block_check_kernel";
+  }
+  if (d_dst) {
+    fp.mode = 1;
+    CU(launch_crc32block_frame(fp, c.sm_count * 8, st));
+    g_launches++;
+  }
+  return CUBEEC_OK;
+}
+
+int crc32block_args(const void* src, size_t len, size_t pitch, size_t block_len, bool framed) {
+  if (!src || len == 0 || ((uintptr_t)src & 15) || (pitch & 15) || pitch < len || len > 0xFFFFFFF0ull) return CUBEEC_ERR_INVALID_ARG;
+  if (!crc32block_valid_len(block_len)) return CUBEEC_ERR_INVALID_ARG;   // crc32block.ErrInvalidBlock (util.go:41-43)
+  if (framed) {
+    const size_t tail = len % block_len;
+    if (tail != 0 && tail <= 4) return CUBEEC_ERR_INVALID_ARG;   // a block without payload: the decoder's ErrMismatchedCrc (request_body.go:118-120)
+  }
+  return CUBEEC_OK;
+}
+}  // namespace
+
+extern "C" size_t cubeec_crc32block_encode_size(size_t n, size_t block_len) {
+  if (!crc32block_valid_len(block_len)) return 0;
+  const size_t payload = block_len - 4;
+  return n + 4 * ((n + payload - 1) / payload);   // crc32block.EncodeSize (util.go:56-63)
+}
+extern "C" size_t cubeec_crc32block_decode_size(size_t total, size_t block_len) {
+  if (!crc32block_valid_len(block_len)) return 0;
+  return total - 4 * ((total + block_len - 1) / block_len);   // crc32block.DecodeSize (util.go:65-71)
+}
+
+extern "C" int cubeec_dev_crc32block_encode(int device, const void* d_src, size_t len, size_t src_pitch, size_t n_buffers,
+                                            size_t block_len, void* d_dst, size_t dst_pitch, int crc_poly, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = crc32block_args(d_src, len, src_pitch, block_len, false))) return rc;
+  if (!d_dst || ((uintptr_t)d_dst & 15) || (dst_pitch & 15) || dst_pitch < cubeec_crc32block_encode_size(len, block_len))
+    return CUBEEC_ERR_INVALID_ARG;
+  if (n_buffers == 0) return CUBEEC_OK;
+  DevCtx* c = ctx_for_device(device);
+  if (!c) return CUBEEC_ERR_INVALID_ARG;
+  CU(cudaSetDevice(device));
+  LaneLease lease;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    if ((rc = lease.acquire(c))) return rc;
+    st = lease.lane->stream;
+  }
+  rc = dev_crc32block_encode_impl(*c, st, (const uint8_t*)d_src, len, src_pitch, n_buffers, block_len, (uint8_t*)d_dst, dst_pitch, crc_poly);
+  if (rc) return rc;
+  if (!stream) CU(cudaStreamSynchronize(st));
+  return CUBEEC_OK;
+}
+
+extern "C" int cubeec_dev_crc32block_decode(int device, const void* d_framed, size_t framed_len, size_t src_pitch, size_t n_buffers,
+                                            size_t block_len, void* d_dst, size_t dst_pitch, int64_t* d_first_bad,
+                                            uint8_t* d_block_ok, int crc_poly, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = crc32block_args(d_framed, framed_len, src_pitch, block_len, true))) return rc;
+  if (d_dst && (((uintptr_t)d_dst & 15) || (dst_pitch & 15) || dst_pitch < cubeec_crc32block_decode_size(framed_len, block_len)))
+    return CUBEEC_ERR_INVALID_ARG;
+  if (n_buffers == 0) return CUBEEC_OK;
+  DevCtx* c = ctx_for_device(device);
+  if (!c) return CUBEEC_ERR_INVALID_ARG;
+  CU(cudaSetDevice(device));
+  LaneLease lease;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    if ((rc = lease.acquire(c))) return rc;
+    st = lease.lane->stream;
+  }
+  rc = dev_crc32block_decode_impl(*c, st, (const uint8_t*)d_framed, framed_len, src_pitch, n_buffers, block_len, (uint8_t*)d_dst,
+                                  dst_pitch, d_first_bad, d_block_ok, crc_poly);
+  if (rc) return rc;
+  if (!stream) CU(cudaStreamSynchronize(st));
+  return CUBEEC_OK;
+}
+
+// Host-pointer forms: one body.  dst needs cubeec_crc32block_encode_size(n) bytes.
+extern "C" int cubeec_crc32block_encode(const uint8_t* src, size_t n, size_t block_len, uint8_t* dst, int crc_poly) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!crc32block_valid_len(block_len)) return CUBEEC_ERR_INVALID_ARG;
+  if (n == 0) return CUBEEC_OK;   // an empty body frames to an empty body
+  if (!src || !dst || n > 0xFFFFFFF0ull) return CUBEEC_ERR_INVALID_ARG;
+  DevCtx* c = g.ctx[0].get();
+  LaneLease lease;
+  if ((rc = lease.acquire(c))) return rc;
+  Lane& l = *lease.lane;
+  const size_t enc = cubeec_crc32block_encode_size(n, block_len);
+  const size_t o_dst = round_up(n, kAlign);
+  if ((rc = lane_reserve(l, o_dst + round_up(enc, kAlign), 256))) return rc;
+  CU(cudaMemcpyAsync(l.d_buf, src, n, cudaMemcpyHostToDevice, l.stream));
+  rc = dev_crc32block_encode_impl(*c, l.stream, l.d_buf, n, o_dst, 1, block_len, l.d_buf + o_dst, round_up(enc, kAlign), crc_poly);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(dst, l.d_buf + o_dst, enc, cudaMemcpyDeviceToHost, l.stream));
+  CU(cudaStreamSynchronize(l.stream));
+  return CUBEEC_OK;
+}
+
+// first_bad: -1 when every block checksum matches, else the index of the first bad block (dst is then still filled:
+// the caller decides, as blockReader.Read stops with ErrMismatchedCrc at that block).  dst may be NULL (verify only).
+extern "C" int cubeec_crc32block_decode(const uint8_t* framed, size_t n_framed, size_t block_len, uint8_t* dst, int64_t* first_bad,
+                                        int crc_poly) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!crc32block_valid_len(block_len) || !first_bad) return CUBEEC_ERR_INVALID_ARG;
+  *first_bad = -1;
+  if (n_framed == 0) return CUBEEC_OK;
+  if (!framed || n_framed > 0xFFFFFFF0ull) return CUBEEC_ERR_INVALID_ARG;
+  const size_t tail = n_framed % block_len;
+  if (tail != 0 && tail <= 4) {   // last block has no payload: ErrMismatchedCrc in the reference (request_body.go:118-120)
+    *first_bad = (int64_t)(n_framed / block_len);
+    return CUBEEC_OK;
+  }
+  DevCtx* c = g.ctx[0].get();
+  LaneLease lease;
+  if ((rc = lease.acquire(c))) return rc;
+  Lane& l = *lease.lane;
+  const size_t dec = cubeec_crc32block_decode_size(n_framed, block_len);
+  const size_t o_dst = round_up(n_framed, kAlign);
+  if ((rc = lane_reserve(l, o_dst + round_up(dec, kAlign) + kAlign, 256))) return rc;
+  CU(cudaMemcpyAsync(l.d_buf, framed, n_framed, cudaMemcpyHostToDevice, l.stream));
+  int64_t* d_bad = reinterpret_cast<int64_t*>(l.d_aux);
+  rc = dev_crc32block_decode_impl(*c, l.stream, l.d_buf, n_framed, o_dst, 1, block_len, dst ? l.d_buf + o_dst : nullptr,
+                                  round_up(dec, kAlign) + kAlign, d_bad, nullptr, crc_poly);
+  if (rc) return rc;
+  if (dst) CU(cudaMemcpyAsync(dst, l.d_buf + o_dst, dec, cudaMemcpyDeviceToHost, l.stream));
+  CU(cudaMemcpyAsync(first_bad, d_bad, sizeof(int64_t), cudaMemcpyDeviceToHost, l.stream));
   CU(cudaStreamSynchronize(l.stream));
   return CUBEEC_OK;
 }

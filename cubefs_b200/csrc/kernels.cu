@@ -6,6 +6,8 @@
 // RS/galois_gen_amd64.s) and Go's hash/crc32 on the BlobStore shard path.  No tensor cores:
 // this is byte-field arithmetic, bounded by HBM bandwidth, LSU (shared-memory lookups) and the
 // integer ALU pipe.  See DESIGN.md for the roofline of each kernel.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace cbe {
@@ -659,7 +661,8 @@ __global__ void __launch_bounds__(kTabThreads) crc_range_kernel(const CrcRangePa
   for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     const uint32_t b = (uint32_t)(unit / p.units_per_buffer), u = (uint32_t)(unit - (uint64_t)b * p.units_per_buffer);
     const uint8_t* buf = p.base + (size_t)b * p.pitch;
-    const size_t a = (size_t)u * p.block;
+    // unit u of a buffer: block bytes from offset + u * stride (crc32block framing: stride = block + 4, offset = 4)
+    const size_t a = (size_t)p.offset + (size_t)u * (p.stride ? p.stride : p.block);
     const size_t e = (a + p.block < p.len) ? a + p.block : p.len;
     // pieces are 16-byte aligned in the address space (base and pitch are 16-aligned)
     const size_t a_al = a & ~(size_t)15;
@@ -696,6 +699,63 @@ __global__ void __launch_bounds__(kTabThreads) crc_range_kernel(const CrcRangePa
 
 cudaError_t launch_crc_ranges(const CrcRangeParams& p, int grid, cudaStream_t stream) {
   crc_range_kernel<<<grid, kTabThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// crc32block framing (blobstore/common/crc32block/block.go:38-49, sized_coder_block.go:43-103, request_body.go:81-130):
+// a body of n bytes becomes blocks of block_len bytes, each [crc32(payload) little endian | payload of up to
+// block_len - 4 bytes].  Payloads are word multiples (block_len is a multiple of 4096), so the copy between the
+// plain and the framed image moves whole 32-bit words; only the final partial word is copied byte by byte.
+//   mode 0 (encode): plain -> framed, block checksums taken from `crcs` (crc_range_kernel over the plain image)
+//   mode 1 (decode): framed -> plain (the checksums are verified separately by crc32block_check_kernel)
+// ------------------------------------------------------------------------------------------
+__global__ void crc32block_frame_kernel(const Crc32BlockParams p) {
+  const uint64_t words_per_buf = (p.plain_len + 3) / 4;
+  const uint64_t total = (uint64_t)p.n_buffers * words_per_buf;
+  const uint32_t pw = (p.block_len - 4) / 4;   // payload words per block
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t b = (uint32_t)(i / words_per_buf);
+    const uint64_t w = i - (uint64_t)b * words_per_buf;
+    const uint32_t u = (uint32_t)(w / pw);
+    const uint64_t plain_off = 4 * w, framed_off = 4 * (w + u + 1);
+    const uint8_t* src = (p.mode == 0 ? p.plain : p.framed) + (size_t)b * (p.mode == 0 ? p.plain_pitch : p.framed_pitch) +
+                         (p.mode == 0 ? plain_off : framed_off);
+    uint8_t* dst = const_cast<uint8_t*>(p.mode == 0 ? p.framed : p.plain) + (size_t)b * (p.mode == 0 ? p.framed_pitch : p.plain_pitch) +
+                   (p.mode == 0 ? framed_off : plain_off);
+    if (plain_off + 4 <= p.plain_len) {
+      *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src);
+    } else {
+      for (uint64_t q = plain_off; q < p.plain_len; q++) dst[q - plain_off] = src[q - plain_off];
+    }
+    if (p.mode == 0 && w == (uint64_t)u * pw) {
+      // first payload word of block u: this thread also writes the block's checksum in front of it
+      *reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(p.framed) + (size_t)b * p.framed_pitch + (size_t)u * p.block_len) =
+          p.crcs[(size_t)b * p.n_blocks + u];
+    }
+  }
+}
+
+// blockUnit.check (block.go:42-49) for every block of every framed buffer: ok[b][u] = (stored == computed);
+// first_bad[b] = index of the first failing block, or -1.
+__global__ void crc32block_check_kernel(const Crc32BlockParams p) {
+  const uint64_t total = (uint64_t)p.n_buffers * p.n_blocks;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t b = (uint32_t)(i / p.n_blocks), u = (uint32_t)(i - (uint64_t)b * p.n_blocks);
+    const uint32_t stored = *reinterpret_cast<const uint32_t*>(p.framed + (size_t)b * p.framed_pitch + (size_t)u * p.block_len);
+    const bool ok = stored == p.crcs[i];
+    if (p.block_ok) p.block_ok[i] = ok ? 1 : 0;
+    if (!ok && p.first_bad) atomicMin(reinterpret_cast<unsigned long long*>(p.first_bad + b), (unsigned long long)u);
+  }
+}
+
+cudaError_t launch_crc32block_frame(const Crc32BlockParams& p, int grid, cudaStream_t stream) {
+  crc32block_frame_kernel<<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_crc32block_check(const Crc32BlockParams& p, cudaStream_t stream) {
+  const uint64_t total = (uint64_t)p.n_buffers * p.n_blocks;
+  crc32block_check_kernel<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 65535), 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -96,7 +96,23 @@ struct CrcRangeParams {
   uint32_t units_per_buffer; // ceil(len/block)
   const CrcDeviceTables* crc;
   uint32_t* out;             // [n_buffers][units_per_buffer] final CRCs of each unit
+  uint32_t stride;           // distance between unit starts (0 = block: units back to back)
+  uint32_t offset;           // start of unit 0 in the buffer
 };
+// crc32block framing kernels (kernels.cu)
+struct Crc32BlockParams {
+  const uint8_t* plain;      // plain image: buffer b at plain + b*plain_pitch, plain_len bytes
+  const uint8_t* framed;     // framed image: buffer b at framed + b*framed_pitch, plain_len + 4*n_blocks bytes
+  size_t plain_pitch, framed_pitch;
+  uint64_t plain_len;
+  uint32_t n_buffers, n_blocks, block_len;
+  int mode;                  // frame kernel: 0 plain -> framed, 1 framed -> plain
+  const uint32_t* crcs;      // [n_buffers][n_blocks] checksums of the payloads
+  uint8_t* block_ok;         // check kernel: optional [n_buffers][n_blocks]
+  int64_t* first_bad;        // check kernel: optional [n_buffers], preset to LLONG_MAX-like "none" by the caller
+};
+cudaError_t launch_crc32block_frame(const Crc32BlockParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_crc32block_check(const Crc32BlockParams& p, cudaStream_t stream);
 cudaError_t launch_crc_ranges(const CrcRangeParams& p, int grid, cudaStream_t stream);
 // whole[b] = combine(units of buffer b); device-side Horner over the per-unit CRCs.
 cudaError_t launch_crc_combine(const uint32_t* unit_crc, uint32_t n_buffers, uint32_t units_per_buffer,

@@ -60,10 +60,12 @@ def load() -> C.CDLL:
     L.cubeec_matrix.argtypes = [vp, vp]
     L.cubeec_decode_matrix.argtypes = [vp, vp, ip, vp]
     L.cubeec_encode.argtypes = [vp, vp, szp, C.c_int, vp, C.c_int]
+    L.cubeec_set_coalescing.argtypes = [C.c_int, C.c_int]
     L.cubeec_verify.argtypes = [vp, vp, szp, C.c_int, ip]
     L.cubeec_reconstruct.argtypes = [vp, vp, szp, C.c_int, C.c_int, vp, vp, C.c_int]
     L.cubeec_encode_contig.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, C.c_size_t, C.c_int]
     L.cubeec_reconstruct_batch.argtypes = [vp, vp, C.c_size_t, C.c_int, vp]
+    L.cubeec_reconstruct_batch_crc.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_int]
     L.cubeec_dev_encode.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp, C.c_int, vp]
     L.cubeec_lrc_encode_contig.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, C.c_int]
     L.cubeec_dev_lrc_encode.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp,
@@ -110,6 +112,11 @@ def last_kernel() -> str:
 def force_kernel(which: int) -> None:
     """Measurement aid: 0 = automatic choice, 1 = generic table kernel only."""
     load().cubeec_debug_force_kernel(which)
+
+
+def set_coalescing(max_batch: int = 32, delay_us: int = 100) -> None:
+    """cubeec_set_coalescing: batching of concurrent single-stripe encode calls (max_batch <= 1: off)."""
+    _check(load().cubeec_set_coalescing(max_batch, delay_us))
 
 
 def lrc_encode_contig(global_eng: "RSEngine", local_eng: "RSEngine", az_count: int, buf: np.ndarray, shard_len: int,
@@ -242,7 +249,87 @@ class RSEngine:
                                            blk.ctypes.data if blk is not None else None, block_payload, poly))
         return crc_out, blk
 
-    def reconstruct_batch(self, stripes, data_only: bool = False, verify: bool = False):
+    def encode_single_call_bench(self, blob: int, thread_counts, seconds: float = 3.0, check: bool = True):
+        """The call shape of access (blobstore/common/ec/encoder.go:114-131): T host threads, each encoding ONE blob
+        per cubeec_encode call (pageable memory, scatter pointers, CRCs requested); the engine's coalescing queue forms
+        the batches.  Returns per T: stripes/s, data GiB/s, p50 / p99 call latency; with the queue switched off for
+        the middle T as a comparison."""
+        import threading
+        import time
+        import zlib
+        k, m = self.k, self.m
+        n = k + m
+        S = max((blob + k - 1) // k, 2048)
+        rng = np.random.default_rng(0xC0BEF5)
+        data = [rng.integers(0, 256, S, dtype=np.uint8) for _ in range(k)]   # shared, read-only (Encode never writes data)
+        L = load()
+
+        def run(T, secs):
+            lat = [[] for _ in range(T)]
+            bufs = [[np.zeros(S, np.uint8) for _ in range(m)] for _ in range(T)]
+            crcs = [np.zeros(n, np.uint32) for _ in range(T)]
+            ptrs, lens = [], []
+            for t in range(T):
+                pa = (C.c_void_p * n)(*([d.ctypes.data for d in data] + [b.ctypes.data for b in bufs[t]]))
+                ptrs.append(pa)
+                lens.append((C.c_size_t * n)(*([S] * n)))
+            stop = [False]
+            errs = []
+            go = threading.Barrier(T + 1)
+
+            def worker(t):
+                go.wait()
+                while not stop[0]:
+                    t0 = time.perf_counter()
+                    rc = L.cubeec_encode(self._h, ptrs[t], lens[t], n, crcs[t].ctypes.data, 0)
+                    lat[t].append(time.perf_counter() - t0)
+                    if rc:
+                        errs.append(rc)
+                        return
+
+            th = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(T)]
+            for x in th:
+                x.start()
+            go.wait()
+            t0 = time.perf_counter()
+            time.sleep(secs)
+            stop[0] = True
+            for x in th:
+                x.join()
+            el = time.perf_counter() - t0
+            if errs:
+                raise CubeecError(errs[0])
+            allv = np.sort(np.concatenate([np.asarray(v) for v in lat if v]))
+            calls = int(allv.size)
+            out = {"threads": T, "calls": calls, "stripes_per_s": round(calls / el, 1),
+                   "data_GiB_per_s": round(calls * k * S / el / (1 << 30), 3),
+                   "p50_ms": round(float(allv[calls // 2]) * 1e3, 3), "p99_ms": round(float(allv[min(calls - 1, int(calls * 0.99))]) * 1e3, 3)}
+            if check:
+                want = [zlib.crc32(d.tobytes()) for d in data]
+                for t in (0, T - 1):
+                    assert [int(c) for c in crcs[t][:k]] == want, "single-call CRC mismatch"
+                    assert all(int(crcs[t][k + r]) == zlib.crc32(bufs[t][r].tobytes()) for r in range(m)), "single-call parity CRC mismatch"
+                    assert all(np.array_equal(bufs[t][r], bufs[0][r]) for r in range(m)), "single-call parity mismatch between threads"
+                out["checked"] = True
+            return out
+
+        res = {"api": "cubeec_encode: one 4 MiB blob per call, pageable host memory, CRCs requested; callers block, the "
+                      "library coalesces (cubeec_set_coalescing default 32 stripes / 100 us)",
+               "shard_bytes": S, "runs": []}
+        run(min(8, max(thread_counts)), 0.5)   # warm-up: pinned staging, lanes
+        for T in thread_counts:
+            res["runs"].append(run(T, seconds))
+        mid = thread_counts[len(thread_counts) // 2]
+        set_coalescing(1, 0)
+        try:
+            r = run(mid, seconds)
+            r["coalescing"] = "off (every call its own H2D / kernel / D2H round trip)"
+            res["runs"].append(r)
+        finally:
+            set_coalescing(32, 100)
+        return res
+
+    def reconstruct_batch(self, stripes, data_only: bool = False, verify: bool = False, crc: bool = False, poly: int = CRC_IEEE):
         """stripes: list of (shards list of np arrays (all allocated), present flags)."""
         n = self.k + self.m
         descs = (StripeDesc * len(stripes))()
@@ -255,6 +342,10 @@ class RSEngine:
             descs[i].present = pres.ctypes.data
             descs[i].shard_len = len(shards[0])
         ok = (C.c_int * len(stripes))() if verify else None
+        if crc:
+            crcs = np.zeros((len(stripes), n), dtype=np.uint32)
+            _check(load().cubeec_reconstruct_batch_crc(self._h, descs, len(stripes), int(data_only), ok, crcs.ctypes.data, poly))
+            return ([bool(v) for v in ok] if verify else None), crcs
         _check(load().cubeec_reconstruct_batch(self._h, descs, len(stripes), int(data_only), ok))
         return [bool(v) for v in ok] if verify else None
 

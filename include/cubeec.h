@@ -101,6 +101,14 @@ int cubeec_decode_matrix(const cubeec_t* h, const uint8_t* present /* k+m */, in
 int cubeec_encode(cubeec_t* h, uint8_t* const* shards, const size_t* lens, int n,
                   uint32_t* crc_out, int crc_poly);
 
+/* Coalescing of concurrent single-stripe cubeec_encode calls (the shape access uses: one blob per Encode call
+ * from up to 1000 goroutines, BS/common/ec/encoder.go:114-131, BS/access/stream/config_defaulter.go:24).  Callers
+ * block in the call; the library gathers up to max_batch stripes of the same code / shard size that arrive within
+ * delay_us of the first one into ONE H2D copy, ONE device encode (+ fused CRC) and ONE D2H copy, staged through
+ * pinned memory that the callers fill and drain in parallel.  Defaults: 32 stripes, 100 us.  max_batch <= 1
+ * disables the queue: every call then performs its own round trip. */
+int cubeec_set_coalescing(int max_batch, int delay_us);
+
 /* reedSolomon.Verify (RS/reedsolomon.go:770-784): *ok = 1 iff parity matches. */
 int cubeec_verify(cubeec_t* h, uint8_t* const* shards, const size_t* lens, int n, int* ok);
 
@@ -149,6 +157,12 @@ typedef struct cubeec_stripe {
  * with independent erasure patterns and lengths.  verify_ok (optional, n entries). */
 int cubeec_reconstruct_batch(cubeec_t* h, const cubeec_stripe_t* stripes, size_t n_stripes,
                              int data_only, int* verify_ok);
+/* The same with the checksums of the repaired shards: the repair worker re-reads every rebuilt
+ * shard on the CPU to checksum it before writing it out (BS/blobnode/worker_slice_recover.go:367-373 after
+ * :865-871).  crc_out: n_stripes*(k+m) entries; only the entries of shards this call regenerated are written
+ * (fused into the reconstruct pass on the device), the others are left untouched. */
+int cubeec_reconstruct_batch_crc(cubeec_t* h, const cubeec_stripe_t* stripes, size_t n_stripes,
+                                 int data_only, int* verify_ok, uint32_t* crc_out, int crc_poly);
 
 /* ---- batched, device-resident (what bench.py's `value` times) ------------------------- */
 
@@ -189,6 +203,33 @@ int cubeec_dev_crc32(int device, const void* d_base, size_t len, size_t pitch, s
                      size_t block_payload /* 0 = whole only */, int crc_poly,
                      uint32_t* d_whole /* n_buffers or NULL */, uint32_t* d_blocks /* or NULL */,
                      void* stream);
+
+/* ---- crc32block framing (BS/common/crc32block) --------------------------------------------- */
+
+/* A body of n bytes is framed into blocks of block_len bytes (a multiple of 4096, default 64 KiB), each
+ * [crc32 of the payload, little endian | up to block_len-4 payload bytes] (block.go:38-49,
+ * sized_coder_block.go:43-103).  This is the body of a shard on disk (datafile.Write, BS/blobnode/core/storage/
+ * datafile.go:337-386) and of an rpc body sent with rpc.WithCrcEncode (BS/common/rpc/client.go:54-65 ->
+ * crc32block.NewBodyEncoder, request_body.go:81-130; block boundaries restart with every body).
+ * EncodeSize / DecodeSize of util.go:56-71; 0 for an invalid block_len. */
+size_t cubeec_crc32block_encode_size(size_t n, size_t block_len);
+size_t cubeec_crc32block_decode_size(size_t total, size_t block_len);
+/* Host pointers, one body: dst receives cubeec_crc32block_encode_size(n, block_len) bytes, byte-identical to
+ * crc32block.NewBodyEncoder / Encoder.Encode. */
+int cubeec_crc32block_encode(const uint8_t* src, size_t n, size_t block_len, uint8_t* dst, int crc_poly);
+/* Verify every block and (dst != NULL) strip the framing.  *first_bad = -1 when all checksums match, else the index
+ * of the first mismatching block (the reference's ErrMismatchedCrc, block.go:42-49 / decode.go:84-107). */
+int cubeec_crc32block_decode(const uint8_t* framed, size_t n_framed, size_t block_len, uint8_t* dst,
+                             int64_t* first_bad, int crc_poly);
+/* Device-resident, many equal-length buffers (buffer b at base + b*pitch; bases and pitches 16-byte aligned):
+ * frame shards that are already in HBM (e.g. right after cubeec_dev_encode), or verify framed shard images the
+ * way datainspect does (BS/blobnode/datainspect.go:246-283): d_first_bad[b] = -1 or the first bad block,
+ * d_block_ok (optional) = one byte per block.  d_dst == NULL: verify only. */
+int cubeec_dev_crc32block_encode(int device, const void* d_src, size_t len, size_t src_pitch, size_t n_buffers,
+                                 size_t block_len, void* d_dst, size_t dst_pitch, int crc_poly, void* stream);
+int cubeec_dev_crc32block_decode(int device, const void* d_framed, size_t framed_len, size_t src_pitch,
+                                 size_t n_buffers, size_t block_len, void* d_dst, size_t dst_pitch,
+                                 int64_t* d_first_bad, uint8_t* d_block_ok, int crc_poly, void* stream);
 
 /* ---- introspection (tests / bench) -------------------------------------------------------- */
 /* Kernels launched by this process so far (all devices). */

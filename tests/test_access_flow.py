@@ -80,10 +80,14 @@ def test_repair_batch_many_bids(cb, oracle):
         for i in bad:
             sh[i][:] = 0
         stripes.append((sh, present))
-    ok = eng.reconstruct_batch(stripes, verify=True)
+    ok, crcs = eng.reconstruct_batch(stripes, verify=True, crc=True)
     assert all(ok)
-    for (sh, _), orig in zip(stripes, originals):
+    for s, ((sh, _), orig) in enumerate(zip(stripes, originals)):
         assert all((a == b).all() for a, b in zip(sh, orig))
+        # the checksums the repair worker needs for the rebuilt shards (worker_slice_recover.go:367-373), from the same call
+        for i in bad:
+            assert int(crcs[s, i]) == zlib.crc32(orig[i].tobytes()), (s, i)
+        assert all(int(crcs[s, i]) == 0 for i in range(k + m) if i not in bad)   # untouched entries
 
 
 def test_in_process_multi_device_partition(oracle):

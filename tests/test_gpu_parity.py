@@ -492,7 +492,10 @@ def test_kernel_selection_and_ab_equivalence(cb, oracle):
         host = rng.integers(0, 256, (ns, n, P), dtype=np.uint8)
         eng = cb.RSEngine(k, m)
         outs = []
-        for force, want in ((0, "rs_bs_kernel<crc>"), (1, "rs_tab_kernel<crc>")):   # CRC always takes the generic table kernel
+        # default: the flat-split fused kernel for shards of 16 KiB and more, the tile-split one (packed mode) below;
+        # 7 = tile-split kernel for every size; 1 = generic table kernel
+        default = "rs_bsf_kernel<crc>" if S >= 16384 else "rs_bs_kernel<crc>"
+        for force, want in ((0, default), (7, "rs_bs_kernel<crc>"), (1, "rs_tab_kernel<crc>")):
             cb.force_kernel(force)
             try:
                 dev = torch.from_numpy(host).cuda()
@@ -503,8 +506,9 @@ def test_kernel_selection_and_ab_equivalence(cb, oracle):
                 outs.append((dev.cpu().numpy(), dcrc.cpu().numpy().view(np.uint32).reshape(ns, n)))
             finally:
                 cb.force_kernel(0)
-        assert (outs[0][0][:, :, :S] == outs[1][0][:, :, :S]).all()
-        assert (outs[0][1] == outs[1][1]).all()
+        for o in outs[1:]:
+            assert (outs[0][0][:, :, :S] == o[0][:, :, :S]).all()
+            assert (outs[0][1] == o[1]).all()
         ora = oracle.RS(k, m)
         for s in range(ns):
             sh = [host[s, i, :S].copy() for i in range(n)]
@@ -612,7 +616,7 @@ def test_small_shards_packed_mode(cb, oracle, km):
         dcrc = torch.zeros(ns * n, dtype=torch.int32, device="cuda")
         eng = cb.RSEngine(k, m)
         eng.dev_encode(dev.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr())
-        assert cb.last_kernel() == "rs_bs_kernel<crc>"
+        assert cb.last_kernel() == ("rs_bsf_kernel<crc>" if S >= 16384 else "rs_bs_kernel<crc>")   # packed mode below 16 KiB
         torch.cuda.synchronize()
         out = dev.cpu().numpy()
         crc = dcrc.cpu().numpy().view(np.uint32).reshape(ns, n)

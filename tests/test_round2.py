@@ -1,0 +1,120 @@
+"""Round-2 GPU tests: the coalescing submit queue under concurrent callers, the ADVICE r1 fixes (replica handles
+with CRC, large batches of small shards through cubeec_encode_contig), big-batch and C4-size oracle checks."""
+import threading
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_shards(rng, k, m, S):
+    return [rng.integers(0, 256, S, dtype=np.uint8) for _ in range(k)] + [np.zeros(S, np.uint8) for _ in range(m)]
+
+
+@pytest.mark.parametrize("coalesce", [(32, 100), (8, 2000), (1, 0)])
+def test_64_concurrent_single_stripe_callers(cb, oracle, coalesce):
+    """64 threads, each calling cubeec_encode on its own stripes (the access call shape, encoder.go:114-131):
+    parity and all CRCs must equal the oracle whatever batches the queue forms; mixed shard sizes and two code
+    modes interleave, so batches of different keys are open at the same time."""
+    cb.set_coalescing(*coalesce)
+    try:
+        engs = {(12, 4): cb.RSEngine(12, 4), (6, 3): cb.RSEngine(6, 3)}
+        errors = []
+
+        def worker(i):
+            try:
+                rng = np.random.default_rng(1000 + i)
+                for it in range(6):
+                    k, m = (12, 4) if (i + it) % 3 else (6, 3)
+                    S = [349526, 65536 + 6, 2048, 21846][(i + it) % 4]
+                    sh = _rand_shards(rng, k, m, S)
+                    want = [s.copy() for s in sh]
+                    oracle.RS(k, m).encode(want)
+                    crc = engs[(k, m)].encode(sh, crc=(it % 2 == 0))
+                    for j in range(k + m):
+                        assert (sh[j] == want[j]).all(), (i, it, j)
+                        if crc is not None:
+                            assert int(crc[j]) == zlib.crc32(want[j].tobytes()), (i, it, j)
+            except Exception as e:   # noqa: BLE001
+                errors.append(repr(e))
+
+        th = [threading.Thread(target=worker, args=(i,)) for i in range(64)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errors, errors[:3]
+    finally:
+        cb.set_coalescing(32, 100)
+
+
+def test_replica_handle_crc(cb):
+    """reedsolomon.New(N, 0) handles (the Replica code modes) with crc_out used to return garbage."""
+    rng = np.random.default_rng(5)
+    for S in (2048, 70001):
+        sh = [rng.integers(0, 256, S, dtype=np.uint8) for _ in range(3)]
+        crc = cb.RSEngine(3, 0).encode(sh, crc=True)
+        assert [int(c) for c in crc] == [zlib.crc32(s.tobytes()) for s in sh]
+        buf = np.concatenate(sh)
+        crc2, _ = cb.RSEngine(3, 0).encode_contig(buf, S, 1, 3 * S, crc=True)
+        assert [int(c) for c in crc2[0]] == [zlib.crc32(s.tobytes()) for s in sh]
+
+
+def test_contig_many_small_stripes_with_crc(cb, oracle):
+    """cubeec_encode_contig + crc_out on a large batch of small shards (packed mode, chunk > 8*SMs)."""
+    k, m, S, ns = 12, 4, 2048, 6000
+    n = k + m
+    rng = np.random.default_rng(11)
+    buf = rng.integers(0, 256, (ns, n * S), dtype=np.uint8)
+    buf[:, k * S:] = 0
+    crc, _ = cb.RSEngine(k, m).encode_contig(buf, S, ns, n * S, crc=True)
+    ora = oracle.RS(k, m)
+    for s in (0, 1, 2999, ns - 1):
+        sh = [buf[s, i * S:(i + 1) * S].copy() for i in range(n)]
+        want = [x.copy() for x in sh[:k]] + [np.zeros(S, np.uint8) for _ in range(m)]
+        ora.encode(want)
+        for i in range(n):
+            assert (sh[i] == want[i]).all(), (s, i)
+            assert int(crc[s, i]) == zlib.crc32(want[i].tobytes()), (s, i)
+
+
+def test_c4_size_vs_oracle(cb, oracle):
+    """BASELINE C4 at its real size: RS(20,4), 1 MiB shards, fused CRC, vs the oracle."""
+    k, m, S = 20, 4, 1 << 20
+    rng = np.random.default_rng(20)
+    sh = _rand_shards(rng, k, m, S)
+    want = [s.copy() for s in sh]
+    oracle.RS(k, m).encode(want)
+    crc = cb.RSEngine(k, m).encode(sh, crc=True)
+    for i in range(k + m):
+        assert (sh[i] == want[i]).all(), i
+        assert int(crc[i]) == zlib.crc32(want[i].tobytes()), i
+
+
+@pytest.mark.parametrize("ns", [1024, 383, 149])
+def test_c2_big_batch_vs_oracle_simd(cb, oracle, ns):
+    """Device-resident C2 batches (the bench shape and the awkward stripe counts) against encode_batch_simd of the
+    oracle: every parity byte and every CRC of every stripe."""
+    import torch
+    k, m, S = 12, 4, 349526
+    n = k + m
+    P = (S + 127) // 128 * 128
+    g = torch.Generator(device="cuda").manual_seed(ns)
+    dev = torch.randint(0, 256, (ns, n, P), dtype=torch.uint8, device="cuda", generator=g)
+    dcrc = torch.zeros(ns * n, dtype=torch.int32, device="cuda")
+    eng = cb.RSEngine(k, m)
+    eng.dev_encode(dev.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr())
+    torch.cuda.synchronize()
+    host = dev.cpu().numpy()
+    crc = dcrc.cpu().numpy().view(np.uint32).reshape(ns, n)
+    ref = host.copy()
+    ref[:, k:, :] = 0
+    rcrc = np.zeros((ns, n), dtype=np.uint32)
+    oracle.RS(k, m).encode_batch_simd(ref, S, P, n * P, ns, threads=8, crc_out=rcrc)
+    assert np.array_equal(host[:, :, :S], ref[:, :, :S])
+    assert np.array_equal(crc, rcrc)
+    # spot-check the oracle's own CRCs against zlib
+    for s in (0, ns - 1):
+        assert int(rcrc[s, 0]) == zlib.crc32(host[s, 0, :S].tobytes())

@@ -53,6 +53,7 @@ def main():
             cb.force_kernel(f)
             batch[:, k:, :].zero_()
             dcrc.zero_()
+            torch.cuda.synchronize()   # the engine runs on its own non-blocking stream when torch's is the legacy default stream
             try:
                 eng.dev_encode(batch.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr(), stream=stream, device=0)
                 torch.cuda.synchronize()
@@ -61,6 +62,18 @@ def main():
                 continue
             par = batch[:, k:, :S].clone()
             crc = dcrc.clone()
+            # independent check of two stripes against the CPU oracle / zlib, and that the data shards were not touched
+            import zlib
+            from oracle import pyoracle
+            orc = None
+            for s_ in (0, ns - 1):
+                h = batch[s_, :, :S].cpu().numpy()
+                want = [h[i].copy() for i in range(k)] + [np.zeros(S, np.uint8) for _ in range(m)]
+                pyoracle.RS(k, m).encode(want)
+                c_ = crc.cpu().numpy().view(np.uint32).reshape(ns, n)[s_]
+                good = all(np.array_equal(h[i], want[i]) for i in range(n)) and all(int(c_[i]) == zlib.crc32(want[i].tobytes()) for i in range(n))
+                orc = good if orc is None else (orc and good)
+            dsum = int(batch[:, :k, :S].to(torch.int64).sum().item())
             ok = True
             detail = None
             if ref_par is None:
@@ -80,6 +93,7 @@ def main():
                     # is the run reproducible?
                     batch[:, k:, :].zero_()
                     dcrc.zero_()
+                    torch.cuda.synchronize()
                     eng.dev_encode(batch.data_ptr(), S, P, n * P, ns, d_crc=dcrc.data_ptr(), stream=stream, device=0)
                     torch.cuda.synchronize()
                     detail["repeat_identical"] = bool(torch.equal(batch[:, k:, :S], par) and torch.equal(dcrc, crc))
@@ -95,7 +109,7 @@ def main():
             ms = e0.elapsed_time(e1) / args.steps
             frac = n * S * ns / (ms * 1e-3) / 1e9 / peak
             print(json.dumps({"force": f, "stripes": ns, "kernel": cb.last_kernel(), "ms": round(ms, 4), "frac": round(frac, 4),
-                              "same_as_first": ok, "detail": detail}), flush=True)
+                              "same_as_first": ok, "oracle_ok": orc, "data_sum": dsum, "detail": detail}), flush=True)
         cb.force_kernel(0)
         del batch
 
