@@ -80,7 +80,11 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  The sampler is started ahead of the
+    region (nvidia-smi takes tens of ms to produce its first line) at a 20 ms period; samples are attributed by their
+    host arrival time, and only those that arrived inside [t0, t1 + one period] count."""
+
+    PERIOD_MS = 20
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
@@ -91,22 +95,31 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", str(self.PERIOD_MS)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t_end = time.perf_counter() + 2.0
+            while not self.rows and time.perf_counter() < t_end:   # wait for the first line
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(2.5 * self.PERIOD_MS / 1e3)
         self.proc.terminate()
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1 + 1.5 * self.PERIOD_MS / 1e3]
+        window = "timed region"
+        if not inside:   # region shorter than a period: the samples on either side of it
+            before = [r for (t, r) in self.rows if t < t0][-1:]
+            after = [r for (t, r) in self.rows if t > t1][:1]
+            inside, window = before + after, "nearest samples around a region shorter than the sampling period"
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -116,7 +129,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -257,7 +270,7 @@ def base_line(args, world, value, ms_per_step):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="encode", choices=["encode", "reconstruct"])
@@ -407,15 +420,17 @@ def main():
     launches0 = cb.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    tw0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    tw1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
     launches = cb.kernel_launches() - launches0
     head_kernel = cb.last_kernel()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -4,9 +4,11 @@ The product is the C-ABI library ``cubefs_b200/lib/libcubeec.so`` (include/cubee
 package is the Python host-side binding used by tests and bench.py:
 
   cubefs_b200.engine    ctypes binding of the C-ABI (RSEngine, crc32, device-resident calls)
-  cubefs_b200.codemode  mirror of blobstore/common/codemode (tactics, LRC layout)
-  cubefs_b200.ec        mirror of blobstore/common/ec (Encoder / LrcEncoder / Buffer sizes)
-  cubefs_b200.crc32block mirror of blobstore/common/crc32block framing on GPU block CRCs
+  cubefs_b200.parallel  stripe partition + coding-matrix broadcast helpers for the one-process-per-GPU runs
+  cubefs_b200.csrc      the CUDA / C++ sources of the library and the XOR-network generator
+
+(The C++/Python mirror of the Go host layer that the reference's tests are replayed through lives in
+tests/mirror/ -- it is test infrastructure, not product.)
 
 There is no CPU compute path: importing works anywhere, calling needs a CUDA device.
 """

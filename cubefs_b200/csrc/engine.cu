@@ -319,6 +319,9 @@ struct cubeec {
     uint32_t* d_pos = nullptr;
     size_t n_pass = 0, n_pat = 0;
     std::vector<int> nin;
+    std::vector<Pattern> h_pat;       // host copy of d_pat ([n_pass][n_pat]): single-pattern plans feed the JIT (jit.cu)
+    std::vector<const void*> jit;     // per pass: run-time compiled kernel of the (only) pattern (nullptr: pass without outputs)
+    int jit_state = 0;                // 0 not tried, 1 ready, 2 unavailable (no NVRTC / compile error): table kernels
   };
   std::vector<std::unique_ptr<Plan>> plans;
   std::mutex mu;
@@ -349,6 +352,35 @@ void make_passes(const std::vector<int>& in_slots, const std::vector<int>& out_s
   }
 }
 
+// The rows that regenerate the missing shards of a presence pattern from the first k present shards
+// (RS/reedsolomon.go:1453-1524): inverse rows for data, parity_row * inverse for parity.
+int decode_rows(int k, int m, const std::vector<uint8_t>& gen, const uint8_t* present, bool data_only, std::vector<int>& valid,
+                std::vector<int>& outs, std::vector<uint8_t>& rows) {
+  const int n = k + m;
+  for (int i = 0; i < n && (int)valid.size() < k; i++)
+    if (present[i]) valid.push_back(i);
+  if ((int)valid.size() < k) return CUBEEC_ERR_TOO_FEW_SHARDS;
+  std::vector<uint8_t> sub((size_t)k * k), dec((size_t)k * k);
+  for (int r = 0; r < k; r++) std::memcpy(&sub[(size_t)r * k], &gen[(size_t)valid[r] * k], (size_t)k);
+  if (!gf_invert(sub.data(), k, dec.data())) return CUBEEC_ERR_SINGULAR;
+  const Gf256& G = gf();
+  for (int i = 0; i < n; i++) {
+    if (present[i]) continue;
+    if (i >= k && data_only) continue;
+    outs.push_back(i);
+    if (i < k) {
+      rows.insert(rows.end(), dec.begin() + (size_t)i * k, dec.begin() + (size_t)(i + 1) * k);
+    } else {
+      for (int c = 0; c < k; c++) {
+        uint8_t v = 0;
+        for (int j = 0; j < k; j++) v ^= G.mul(gen[(size_t)i * k + j], dec[(size_t)j * k + c]);
+        rows.push_back(v);
+      }
+    }
+  }
+  return CUBEEC_OK;
+}
+
 // Presence pattern -> fused decode passes: every missing shard expressed directly over the
 // first k present shards (data rows from the inverse, RS/reedsolomon.go:1469-1524; parity rows
 // pre-multiplied: parity_row * decode, same values as the reference's second pass :1531-1550).
@@ -362,30 +394,10 @@ int decode_passes(cubeec* h, const uint8_t* present, bool data_only, std::vector
     auto it = h->dec_cache.find(key);
     if (it != h->dec_cache.end()) { passes = it->second; return CUBEEC_OK; }
   }
-  std::vector<int> valid;
-  for (int i = 0; i < n && (int)valid.size() < k; i++)
-    if (present[i]) valid.push_back(i);
-  if ((int)valid.size() < k) return CUBEEC_ERR_TOO_FEW_SHARDS;
-  std::vector<uint8_t> sub((size_t)k * k), dec((size_t)k * k);
-  for (int r = 0; r < k; r++) std::memcpy(&sub[(size_t)r * k], &h->gen[(size_t)valid[r] * k], (size_t)k);
-  if (!gf_invert(sub.data(), k, dec.data())) return CUBEEC_ERR_SINGULAR;
-  std::vector<int> outs;
+  std::vector<int> valid, outs;
   std::vector<uint8_t> rows;
-  const Gf256& G = gf();
-  for (int i = 0; i < n; i++) {
-    if (present[i]) continue;
-    if (i >= k && data_only) continue;
-    outs.push_back(i);
-    if (i < k) {
-      rows.insert(rows.end(), dec.begin() + (size_t)i * k, dec.begin() + (size_t)(i + 1) * k);
-    } else {
-      for (int c = 0; c < k; c++) {
-        uint8_t v = 0;
-        for (int j = 0; j < k; j++) v ^= G.mul(h->gen[(size_t)i * k + j], dec[(size_t)j * k + c]);
-        rows.push_back(v);
-      }
-    }
-  }
+  int rc = decode_rows(k, h->m, h->gen, present, data_only, valid, outs, rows);
+  if (rc) return rc;
   make_passes(valid, outs, rows, false, passes);
   std::lock_guard<std::mutex> lk(h->mu);
   if (h->dec_cache.size() > 8192) h->dec_cache.clear();
@@ -867,6 +879,32 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
 
 extern "C" void cubeec_debug_force_kernel(int which) { g_force_kernel.store(which); }
 
+// CPU-side check of the run-time code generator (tests, no device needed): builds the decode rows of RS(k, m) for
+// the presence pattern the way cubeec_dev_reconstruct does and compiles the specialised kernel with NVRTC.
+// 0 = compiled, 1 = NVRTC not installed, 2 = compile error, else a CUBEEC_ERR_* of the pattern itself.
+extern "C" int cubeec_debug_jit_check(int k, int m, const uint8_t* present, int data_only, char* log, size_t log_cap) {
+  if (k <= 0 || m < 0 || k + m > 256 || !present) return CUBEEC_ERR_INVALID_ARG;
+  std::vector<uint8_t> gen;
+  if (!build_generator(k, k + m, gen)) return CUBEEC_ERR_SINGULAR;
+  std::vector<int> valid, outs;
+  std::vector<uint8_t> rows;
+  int rc = decode_rows(k, m, gen, present, data_only != 0, valid, outs, rows);
+  if (rc) return rc;
+  std::string err;
+  int result = 0;
+  for (size_t o0 = 0; o0 < outs.size() && result == 0; o0 += kMaxOut) {
+    const size_t no = std::min<size_t>(kMaxOut, outs.size() - o0);
+    std::vector<uint8_t> ins(valid.begin(), valid.end()), os(outs.begin() + (long)o0, outs.begin() + (long)(o0 + no));
+    std::vector<uint8_t> rr(rows.begin() + (long)(o0 * k), rows.begin() + (long)((o0 + no) * k));
+    result = jit_compile_check(ins, os, rr, nullptr, &err);
+  }
+  if (log && log_cap) {
+    std::strncpy(log, err.c_str(), log_cap - 1);
+    log[log_cap - 1] = 0;
+  }
+  return result ? result + 100 : 0;   // 101 = NVRTC missing, 102 = compile error
+}
+
 // ------------------------------------------------------------------------------------------
 // process-wide API
 // ------------------------------------------------------------------------------------------
@@ -1311,7 +1349,68 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
     CU(cudaMalloc(&fresh->d_pos, n_stripes * sizeof(uint32_t)));
     CU(cudaMemcpy(fresh->d_pat, flat.data(), flat.size() * sizeof(Pattern), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(fresh->d_pos, pos.data(), n_stripes * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    fresh->h_pat = flat;
     plan = fresh.get();
+  }
+  // One erasure pattern for the whole batch (a repair task: one broken vuid, worker_slice_recover.go:822-871):
+  // run the kernel compiled for exactly these decode rows (jit.cu); ~1 s once per pattern, cached.
+  static const bool jit_env_off = getenv("CUBEEC_NO_JIT") != nullptr;
+  const int fk = g_force_kernel.load();
+  if (plan->n_pat == 1 && !jit_env_off && fk != 1 && fk != 3 && fk != 4 &&
+      bs_layout_ok((const uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch)) {
+    if (plan->jit_state == 0) {
+      std::vector<const void*> ks;
+      bool ok = true;
+      for (size_t j = 0; j < plan->n_pass && ok; j++) {
+        const Pattern& pt = plan->h_pat[j];
+        if (pt.n_out == 0) { ks.push_back(nullptr); continue; }
+        std::vector<uint8_t> ins(pt.in_slot, pt.in_slot + pt.n_in), outs(pt.out_slot, pt.out_slot + pt.n_out), rows;
+        for (int r = 0; r < pt.n_out; r++) rows.insert(rows.end(), pt.coef[r], pt.coef[r] + pt.n_in);
+        std::string err;
+        const void* kf = jit_kernel(device, ins, outs, rows, &err);
+        if (!kf) { ok = false; t_last_error = err; }
+        ks.push_back(kf);
+      }
+      std::lock_guard<std::mutex> lk(h->mu);
+      plan->jit = ks;
+      plan->jit_state = ok ? 1 : 2;
+    }
+    if (plan->jit_state == 1) {
+      LaneLease jl;
+      cudaStream_t js = (cudaStream_t)stream;
+      if (!js) {
+        if ((rc = jl.acquire(c))) return rc;
+        js = jl.lane->stream;
+      }
+      JitParams jp;
+      std::memset(&jp, 0, sizeof(jp));
+      jp.base = (uint8_t*)d_base;
+      jp.stripe_pitch = stripe_pitch;
+      jp.shard_pitch = shard_pitch;
+      jp.shard_len = (uint32_t)shard_len;
+      jp.n_stripes = (uint32_t)n_stripes;
+      jp.units_per_shard = (uint32_t)((shard_len + 1023) / 1024);
+      jp.total_units = (uint64_t)n_stripes * jp.units_per_shard;
+      const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((jp.total_units + 15) / 16, (uint64_t)c->sm_count));
+      for (size_t j = 0; j < plan->n_pass; j++) {
+        if (!plan->jit[j]) continue;
+        CU(jit_launch(plan->jit[j], jp, grid, js));
+        g_launches++;
+      }
+      t_last_kernel = "rs_jit_kernel";
+      if (fresh) {
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (h->plans.size() < 16) {
+          h->plans.push_back(std::move(fresh));
+        } else {
+          CU(cudaStreamSynchronize(js));
+          cudaFree(fresh->d_pat);
+          cudaFree(fresh->d_pos);
+        }
+      }
+      if (!stream) CU(cudaStreamSynchronize(js));
+      return CUBEEC_OK;
+    }
   }
   LaneLease lease;
   cudaStream_t st = (cudaStream_t)stream;

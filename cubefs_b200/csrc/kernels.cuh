@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <cstddef>
 #include <cstdint>
+#include <string>
+#include <vector>
 
 namespace cbe {
 
@@ -227,6 +229,21 @@ struct BsgParams {
 uint32_t bsg_units_per_shard(size_t shard_len);
 // max_out: largest n_out of any pattern of the launch (1..4); mode 0 = store outputs, 1 = compare with stored
 cudaError_t launch_bsg(const BsgParams& p, int max_out, int mode, int grid, cudaStream_t st);
+
+// ---- run-time compiled pattern kernels (jit.cu) --------------------------------------------------------
+struct JitParams {   // layout mirrored in the generated source (jit.cu: kPrologue)
+  uint8_t* base;
+  uint64_t stripe_pitch, shard_pitch;
+  uint32_t shard_len, n_stripes;
+  uint32_t units_per_shard, pad;     // units of 1 KiB
+  uint64_t total_units;
+};
+bool jit_available();
+const void* jit_kernel(int device, const std::vector<uint8_t>& in_slots, const std::vector<uint8_t>& out_slots,
+                       const std::vector<uint8_t>& rows, std::string* err);
+int jit_compile_check(const std::vector<uint8_t>& in_slots, const std::vector<uint8_t>& out_slots, const std::vector<uint8_t>& rows,
+                      std::string* source, std::string* err);
+cudaError_t jit_launch(const void* kern, const JitParams& p, int grid, cudaStream_t st);
 
 // ---- bit-sliced syndrome reconstruct (bitslice.cu) ---------------------------------------------
 // The reference decodes from the first k present shards (RS/reedsolomon.go:1453-1465).  Data indices

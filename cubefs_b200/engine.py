@@ -316,8 +316,8 @@ class RSEngine:
         res = {"api": "cubeec_encode: one 4 MiB blob per call, pageable host memory, CRCs requested; callers block, the "
                       "library coalesces (cubeec_set_coalescing default 32 stripes / 100 us)",
                "shard_bytes": S, "runs": []}
-        run(min(8, max(thread_counts)), 0.5)   # warm-up: pinned staging, lanes
         for T in thread_counts:
+            run(T, 0.7)   # warm-up at this concurrency: pinned staging buffers of the batches, lanes, thread start-up
             res["runs"].append(run(T, seconds))
         mid = thread_counts[len(thread_counts) // 2]
         set_coalescing(1, 0)

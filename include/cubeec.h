@@ -239,8 +239,14 @@ const char* cubeec_last_kernel(void);
 /* Measurement aid: 0 = automatic kernel choice (default), 1 = no bit-sliced kernels, 2 = bit-sliced
  * syndrome kernel for cubeec_dev_reconstruct, 3 = generic (runtime-arity) table kernel only,
  * 5 = warp-specialised fused encode+CRC kernel (rs_bsw_kernel, RS(12,4) only) instead of rs_bs_kernel<crc>,
- * 6 = rolled-loop fused encode+CRC kernel (smaller hot loop; RS(12,4), (10,4), (6,2)). */
+ * 6 = rolled-loop fused encode+CRC kernel (smaller hot loop; RS(12,4), (10,4), (6,2)),
+ * 7 = tile-split fused kernel rs_bs_kernel<crc> for every shard size (default: the flat-split rs_bsf_kernel from
+ * 16 KiB), 1000+T = flat-split fused kernel with T threads per CTA (RS(12,4) only),
+ * 4 = no run-time compiled (NVRTC) reconstruct kernels: single-pattern batches take the table kernels too. */
 void cubeec_debug_force_kernel(int which);
+/* Tests: generate and NVRTC-compile (no device needed) the run-time specialised reconstruct kernel of RS(k, m) for
+ * a presence pattern.  0 = compiled, 101 = NVRTC not installed, 102 = compile error (log), else CUBEEC_ERR_*. */
+int cubeec_debug_jit_check(int k, int m, const uint8_t* present, int data_only, char* log, size_t log_cap);
 
 #ifdef __cplusplus
 }

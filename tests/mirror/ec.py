@@ -1,4 +1,4 @@
-"""Python view of the C++ host mirror (cubefs_b200/host/cubefs_ec.{hpp,cc}): the BlobStore
+"""TEST INFRASTRUCTURE, not product: Python view of the C++ host mirror (tests/mirror/cubefs_ec.{hpp,cc}): the BlobStore
 packages directly above the libcubeec C-ABI -- blobstore/common/{codemode,ec,crc32block} -- with the
 reference's names and error behaviour.  Used by tests/test_host_mirror.py.
 
@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from .engine import load as _load_engine
+from cubefs_b200.engine import load as _load_engine
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "lib", "libcubefs_host.so")

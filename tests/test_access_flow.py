@@ -11,7 +11,7 @@ import zlib
 import numpy as np
 import pytest
 
-from cubefs_b200 import ec as cm
+from mirror import ec as cm
 
 pytestmark = pytest.mark.gpu
 

@@ -61,3 +61,27 @@ def test_product_never_imports_oracle():
                         if re.search(r"^\s*(#\s*include|import|from)\b.*oracle|(dlopen|CDLL)\(.*oracle|-l\S*oracle", line):
                             bad.append((f, line.strip()))
     assert not bad, bad
+
+
+def test_runtime_codegen_compiles_for_every_erasure_class(cb):
+    """The NVRTC-specialised reconstruct kernels (csrc/jit.cu): generate + compile the source for single, double,
+    triple and quadruple erasures, data-only, and the m > 4 codes (several passes).  No device is needed to compile."""
+    import ctypes as C
+
+    import numpy as np
+    L = cb.load()
+    L.cubeec_debug_jit_check.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
+    cases = [(12, 4, [3], 0), (12, 4, [1, 7, 13], 0), (12, 4, [0, 1, 2, 3], 0), (12, 4, [0, 13], 1), (6, 3, [8], 0),
+             (4, 2, [0, 5], 0), (6, 10, [0, 1, 2, 3, 4, 7, 9], 0), (3, 1, [1], 0)]
+    for k, m, miss, data_only in cases:
+        pres = np.ones(k + m, np.uint8)
+        pres[miss] = 0
+        log = C.create_string_buffer(8000)
+        rc = L.cubeec_debug_jit_check(k, m, pres.ctypes.data, data_only, log, 8000)
+        if rc == 101:
+            pytest.skip("libnvrtc is not installed here: the engine falls back to the table kernels")
+        assert rc == 0, (k, m, miss, rc, log.value[:2000])
+    # too few survivors is reported as such, before any code generation
+    pres = np.ones(6, np.uint8)
+    pres[[0, 1, 2]] = 0
+    assert L.cubeec_debug_jit_check(4, 2, pres.ctypes.data, 0, None, 0) == 3

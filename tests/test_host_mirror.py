@@ -8,7 +8,7 @@ import zlib
 import numpy as np
 import pytest
 
-from cubefs_b200 import ec as cm   # codemode + ec + crc32block mirror
+from mirror import ec as cm   # codemode + ec + crc32block mirror
 
 SRC = bytes(range(256)) * 3 + b"cubefs-blobstore-ec-src-data" * 5   # encoder_test.go's srcData stand-in
 

@@ -2,7 +2,12 @@
 """BASELINE configs C4/C5: device-resident encode throughput over shard sizes and code modes.
 
 python tools/sweep.py [--gpu 0] [--crc 1]   -> one JSON line per (k, m, S) with GiB/s of data and
-the fraction of the measured HBM peak ((k+m)*S per stripe of algorithmic traffic)."""
+the fraction of the measured HBM peak ((k+m)*S per stripe of algorithmic traffic).
+
+8 GPUs: python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1
+--master-port 29511 tools/sweep.py   -> every rank runs the same cases on its own GPU (stripes are independent: the batch
+is partitioned, no data-path collective), a barrier brackets each timing, the time of a case is the MAX over ranks and
+rank 0 prints the aggregate (sum of all ranks' bytes / that time) next to the per-GPU roofline fraction."""
 import argparse
 import json
 import os
@@ -23,6 +28,27 @@ def peak():
         return 6650.0
 
 
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+
+
+def sync_max_ms(ms, dev):
+    """a multi-GPU case takes as long as its slowest rank"""
+    if WORLD == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(dev):
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+
+
 def run(eng, k, m, S, crc, total_bytes, dev, steps=5):
     n = k + m
     P = (S + 127) // 128 * 128
@@ -36,13 +62,13 @@ def run(eng, k, m, S, crc, total_bytes, dev, steps=5):
     for _ in range(3):
         step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(dev)
+    barrier(dev)
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / steps
+    barrier(dev)
+    ms = sync_max_ms(e0.elapsed_time(e1) / steps, dev)
     return ns, ms, cb.last_kernel()
 
 
@@ -55,6 +81,11 @@ def main():
                     help="instead of the C4/C5 shard-size sweep: every predefined EC code mode (codemode.go:65-94) at "
                          "1 MiB shards, bit-sliced path and (A/B) the table kernels")
     args = ap.parse_args()
+    if WORLD > 1:
+        import torch.distributed as dist
+        args.gpu = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(args.gpu)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", args.gpu))
     dev = torch.device("cuda", args.gpu)
     torch.cuda.set_device(dev)
     cb.init([args.gpu])
@@ -92,7 +123,8 @@ def main():
                 torch.cuda.synchronize(dev)
                 ms = e0.elapsed_time(e1) / 5
                 moved = n * S * ns / (ms * 1e-3) / 1e9
-                print(json.dumps({"lrc": [N, M, L, az], "shard_bytes": S, "stripes": ns, "crc": bool(crc), "kernel": cb.last_kernel(),
+                if RANK == 0:
+                  print(json.dumps({"lrc": [N, M, L, az], "shard_bytes": S, "stripes": ns, "crc": bool(crc), "kernel": cb.last_kernel(),
                                   "ms": round(ms, 4), "data_GiB_s": round(N * S * ns / (ms * 1e-3) / 2**30, 1),
                                   "moved_GB_s": round(moved, 1), "frac_of_measured_hbm": round(moved / pk, 4)}), flush=True)
     engines = {}
@@ -103,9 +135,14 @@ def main():
             ns, ms, kern = run(eng, k, m, S, crc, args.gib * (1 << 30), dev)
             cb.force_kernel(0)
             moved = (k + m) * S * ns / (ms * 1e-3) / 1e9
-            print(json.dumps({"k": k, "m": m, "shard_bytes": S, "stripes": ns, "crc": bool(crc), "kernel": kern,
-                              "ms": round(ms, 4), "data_GiB_s": round(k * S * ns / (ms * 1e-3) / 2**30, 1),
-                              "moved_GB_s": round(moved, 1), "frac_of_measured_hbm": round(moved / pk, 4)}), flush=True)
+            if RANK == 0:
+                print(json.dumps({"k": k, "m": m, "shard_bytes": S, "stripes_per_gpu": ns, "n_gpus": WORLD, "crc": bool(crc), "kernel": kern,
+                                  "ms": round(ms, 4), "data_GiB_s_all_gpus": round(WORLD * k * S * ns / (ms * 1e-3) / 2**30, 1),
+                                  "moved_GB_s_per_gpu": round(moved, 1), "frac_of_measured_hbm": round(moved / pk, 4),
+                                  "frac_nominal_8TBs": round(moved / 8000.0, 4)}), flush=True)
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
