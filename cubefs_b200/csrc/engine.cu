@@ -117,10 +117,28 @@ struct DevCtx {
   std::condition_variable cv;
   std::vector<Lane*> free_lanes;
   int lanes_created = 0;
-  std::mutex bulk_mu;   // one multi-lane (batched) operation per device at a time
+  // Multi-lane (batched) operations take one of kBulkSlots slots before their lanes: bounded staging memory, and
+  // no caller ever waits for a lane while holding some (kBulkSlots * 3 + coalescing workers <= kLanesPerDevice).
+  int bulk_free = 4;
 };
 
 constexpr int kLanesPerDevice = 16;
+
+struct BulkSlot {
+  DevCtx* c;
+  explicit BulkSlot(DevCtx* ctx) : c(ctx) {
+    std::unique_lock<std::mutex> lk(c->mu);
+    c->cv.wait(lk, [&] { return c->bulk_free > 0; });
+    c->bulk_free--;
+  }
+  BulkSlot(const BulkSlot&) = delete;
+  BulkSlot& operator=(const BulkSlot&) = delete;
+  ~BulkSlot() {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->bulk_free++;
+    c->cv.notify_all();
+  }
+};
 
 struct Global {
   std::mutex mu;
@@ -264,7 +282,7 @@ struct LaneLease {
     if (c && lane) {
       std::lock_guard<std::mutex> lk(c->mu);
       c->free_lanes.push_back(lane);
-      c->cv.notify_one();
+      c->cv.notify_all();
     }
   }
 };
@@ -1884,8 +1902,8 @@ extern "C" int cubeec_reconstruct_batch_crc(cubeec_t* h, const cubeec_stripe_t* 
   // Stripes are dealt round-robin to (device, lane) pairs; stream order keeps each lane's
   // staging buffer safe for reuse, so the host never waits between stripes.
   const size_t n_ctx = g.ctx.size();
-  std::vector<std::unique_ptr<std::lock_guard<std::mutex>>> bulk;
-  for (size_t ci = 0; ci < n_ctx; ci++) bulk.push_back(std::make_unique<std::lock_guard<std::mutex>>(g.ctx[ci]->bulk_mu));
+  std::vector<std::unique_ptr<BulkSlot>> bulk;   // context order: no cycle between concurrent batch calls
+  for (size_t ci = 0; ci < n_ctx; ci++) bulk.push_back(std::make_unique<BulkSlot>(g.ctx[ci].get()));
   std::vector<std::unique_ptr<LaneLease>> leases;
   for (size_t ci = 0; ci < n_ctx; ci++)
     for (int q = 0; q < 2; q++) {
@@ -1948,7 +1966,7 @@ int encode_contig_device(cubeec* h, DevCtx* c, uint8_t* base, size_t S, size_t f
   const int k = h->k, n = hl ? y->N + y->M + y->L : h->k + h->m, m = n - k;
   const size_t P = round_up(S, kAlign);
   const size_t dstripe = P * n;
-  std::lock_guard<std::mutex> bulk(c->bulk_mu);
+  BulkSlot bulk(c);   // up to 4 batched calls per device stage and compute concurrently
   // chunk: ~192 MiB of device staging per lane (measured 32: 37.4, 96: 39.7, 192: 40.2 GiB/s end to end) -- small enough that the fill / drain of the
   // H2D -> kernel -> D2H pipeline is a small part of a batch, large enough to amortise launches
   // (CUBEEC_CONTIG_CHUNK_MB / CUBEEC_CONTIG_LANES: measurement knobs, defaults are the tuned values)
