@@ -12,5 +12,5 @@ tests/mirror/ -- it is test infrastructure, not product.)
 
 There is no CPU compute path: importing works anywhere, calling needs a CUDA device.
 """
-from .engine import (CubeecError, RSEngine, crc32, crc32_blocks, dev_lrc_encode, device_count, force_kernel,  # noqa: F401
+from .engine import (CubeecError, RSEngine, crc32, crc32_blocks, dev_lrc_encode, dev_lrc_reconstruct, dev_lrc_verify, device_count, force_kernel,  # noqa: F401
                      init, kernel_launches, last_kernel, lib_path, load, lrc_encode_contig, set_coalescing)

@@ -77,8 +77,8 @@ __host__ __device__ __forceinline__ uint64_t bsf_owner(uint64_t u, uint64_t U, u
 
 // CRC: 1 = every shard, 2 = the M outputs only (later passes of an m > 4 code, LRC local stripes).
 // RD = number of 256-bit load buffers (RD - 1 shards in flight ahead of the one being coded).
-template <int K, int M, int V, int CRC, int NT, int RD = (NT <= 384 ? 4 : 3)>
-__global__ void __launch_bounds__(NT, 1) rs_bsf_kernel(const BsfParams p) {
+template <int K, int M, int V, int CRC, int NT, int RD>
+__device__ __forceinline__ void bsf_body(const BsfParams& p) {
   static_assert(CRC == 1 || CRC == 2, "fused-CRC kernel");
   static_assert(K >= 2 && K + M <= 32, "lane q publishes the remainder of shard q");
   static_assert(RD >= 3 && K >= RD - 1, "load ring");
@@ -335,9 +335,28 @@ __global__ void __launch_bounds__(NT, 1) rs_bsf_kernel(const BsfParams p) {
     flush(t == 0 ? s - 1 : s);   // (s, t) is one unit past the run: the last unit's stripe
   }
 }
+template <int K, int M, int V, int CRC, int NT, int RD = (NT <= 384 ? 4 : 3)>
+__global__ void __launch_bounds__(NT, 1) rs_bsf_kernel(const BsfParams p) {
+  bsf_body<K, M, V, CRC, NT, RD>(p);
+}
+// the same body with an explicit register cap, for warp counts whose natural cap ptxas rounds away (A/B aid)
+template <int K, int M, int V, int CRC, int NT, int RD, int NREG>
+__global__ void __maxnreg__(NREG) rs_bsf_kernel_mr(const BsfParams p) {
+  bsf_body<K, M, V, CRC, NT, RD>(p);
+}
+
 template <int K, int M, int V, int MODE, int NT = kBsfThreads>
 static cudaError_t bsf_launch_one(const BsfParams& p, int grid, cudaStream_t st) {
   auto kern = rs_bsf_kernel<K, M, V, MODE, NT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsfSmemBytes);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, NT, kBsfSmemBytes, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int NT, int RD, int NREG>
+static cudaError_t bsf_launch_mr(const BsfParams& p, int grid, cudaStream_t st) {
+  auto kern = rs_bsf_kernel_mr<12, 4, 0, 1, NT, RD, NREG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsfSmemBytes);
   if (e != cudaSuccess) return e;
   kern<<<grid, NT, kBsfSmemBytes, st>>>(p);

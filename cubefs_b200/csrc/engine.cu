@@ -337,6 +337,7 @@ struct cubeec {
     uint32_t* d_pos = nullptr;
     size_t n_pass = 0, n_pat = 0;
     std::vector<int> nin;
+    std::vector<uint8_t> slot_map;    // empty = identity; else shard i of the code is slot_map[i] of the stripe (LRC local stripes)
     std::vector<Pattern> h_pat;       // host copy of d_pat ([n_pass][n_pat]): single-pattern plans feed the JIT (jit.cu)
     std::vector<const void*> jit;     // per pass: run-time compiled kernel of the (only) pattern (nullptr: pass without outputs)
     int jit_state = 0;                // 0 not tried, 1 ready, 2 unavailable (no NVRTC / compile error): table kernels
@@ -1197,6 +1198,100 @@ extern "C" int cubeec_dev_lrc_encode(cubeec_t* global, cubeec_t* local, int az_c
   return CUBEEC_OK;
 }
 
+static int dev_reconstruct_core(cubeec_t* h, DevCtx* c, int device, void* d_base, size_t shard_len, size_t shard_pitch,
+                                size_t stripe_pitch, size_t n_stripes, const uint8_t* present, int data_only, void* stream,
+                                const uint8_t* slot_map);
+
+// ------------------------------------------------------------------------------------------
+// LRC Verify / Reconstruct on the device-resident stripe (lrcEncoder.Verify / Reconstruct / ReconstructData,
+// blobstore/common/ec/lrcencoder.go:87-200): the global RS(N, M) over the first N+M shards, then per AZ the local
+// RS((N+M)/AZ, L/AZ) over that AZ's shard list (codemode.GetECLayoutByAZ) -- the composition the reference does with
+// 1 + AZCount engine calls, each of which would stage its shards over PCIe again through the plain ABI.
+// ------------------------------------------------------------------------------------------
+extern "C" int cubeec_dev_lrc_verify(cubeec_t* global, cubeec_t* local, int az_count, int device, const void* d_base,
+                                     size_t shard_len, size_t shard_pitch, size_t stripe_pitch, size_t n_stripes, int32_t* d_ok,
+                                     void* stream) {
+  LrcLayout y;
+  int rc = lrc_layout(global, local, az_count, &y);
+  if (rc) return rc;
+  if (!d_ok) return CUBEEC_ERR_INVALID_ARG;
+  if ((rc = ensure_init())) return rc;
+  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch, y.N + y.M + y.L, n_stripes))) return rc;
+  if (n_stripes == 0) return CUBEEC_OK;
+  DevCtx* c = ctx_for_device(device);
+  if (!c) return CUBEEC_ERR_INVALID_ARG;
+  CU(cudaSetDevice(device));
+  if (!global->bs_passes_plain || !local->bs_passes_plain || !bs_layout_ok((const uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch)) {
+    t_last_error = "LRC device path needs the generated networks of both codes and a 32-byte aligned layout";
+    return CUBEEC_ERR_UNSUPPORTED;
+  }
+  LaneLease lease;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    if ((rc = lease.acquire(c))) return rc;
+    st = lease.lane->stream;
+  }
+  const int n_slots = y.N + y.M + y.L;
+  const Geometry gm = bs_geometry(*c, shard_len, n_stripes);
+  // d_ok doubles as the mismatch flag array: every code of the stripe raises the same flag, then it is inverted
+  CU(cudaMemsetAsync(d_ok, 0, n_stripes * sizeof(int32_t), st));
+  rc = bs_run(global, *c, st, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, gm, n_slots, nullptr, y.N, 0, nullptr, 0,
+              true, d_ok);
+  if (rc) return rc;
+  for (int a = 0; a < y.az; a++) {
+    uint8_t in_slots[64];
+    int q = 0;
+    for (int i = 0; i < y.N / y.az; i++) in_slots[q++] = (uint8_t)(a * (y.N / y.az) + i);
+    for (int i = 0; i < y.M / y.az; i++) in_slots[q++] = (uint8_t)(y.N + a * (y.M / y.az) + i);
+    rc = bs_run(local, *c, st, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, gm, n_slots, in_slots,
+                y.N + y.M + a * y.ml, 0, nullptr, 0, true, d_ok);
+    if (rc) return rc;
+  }
+  CU(launch_invert_flags(d_ok, n_stripes, st));
+  g_launches++;
+  if (!stream) CU(cudaStreamSynchronize(st));
+  return CUBEEC_OK;
+}
+
+// present: HOST array n_stripes*(N+M+L).  Global shards are regenerated from the global code (as lrcEncoder.Reconstruct
+// does first, lrcencoder.go:152-157: local parity never helps the global decode), then every missing local parity shard
+// from its AZ's (now complete) shards (:159-183).  data_only = lrcEncoder.ReconstructData (:185-200): global data only.
+extern "C" int cubeec_dev_lrc_reconstruct(cubeec_t* global, cubeec_t* local, int az_count, int device, void* d_base,
+                                          size_t shard_len, size_t shard_pitch, size_t stripe_pitch, size_t n_stripes,
+                                          const uint8_t* present, int data_only, void* stream) {
+  LrcLayout y;
+  int rc = lrc_layout(global, local, az_count, &y);
+  if (rc) return rc;
+  if (!present) return CUBEEC_ERR_INVALID_ARG;
+  if ((rc = ensure_init())) return rc;
+  const int n_slots = y.N + y.M + y.L, ng = y.N + y.M, nl = y.kl + y.ml;
+  if ((rc = check_dev_layout(d_base, shard_len, shard_pitch, stripe_pitch, n_slots, n_stripes))) return rc;
+  if (n_stripes == 0) return CUBEEC_OK;
+  DevCtx* c = ctx_for_device(device);
+  if (!c) return CUBEEC_ERR_INVALID_ARG;
+  CU(cudaSetDevice(device));
+  std::vector<uint8_t> pg(n_stripes * (size_t)ng);
+  for (size_t s = 0; s < n_stripes; s++)
+    for (int i = 0; i < ng; i++) pg[s * ng + i] = present[s * n_slots + i] ? 1 : 0;
+  rc = dev_reconstruct_core(global, c, device, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, pg.data(), data_only, stream, nullptr);
+  if (rc || data_only) return rc;
+  for (int a = 0; a < y.az; a++) {
+    std::vector<uint8_t> map(nl), pl(n_stripes * (size_t)nl, 1);
+    int q = 0;
+    for (int i = 0; i < y.N / y.az; i++) map[q++] = (uint8_t)(a * (y.N / y.az) + i);
+    for (int i = 0; i < y.M / y.az; i++) map[q++] = (uint8_t)(y.N + a * (y.M / y.az) + i);
+    for (int i = 0; i < y.ml; i++) map[q++] = (uint8_t)(ng + a * y.ml + i);
+    bool any = false;
+    for (size_t s = 0; s < n_stripes; s++)
+      for (int i = 0; i < y.ml; i++)
+        if (!present[s * n_slots + ng + a * y.ml + i]) { pl[s * nl + y.kl + i] = 0; any = true; }
+    if (!any) continue;
+    rc = dev_reconstruct_core(local, c, device, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, pl.data(), 0, stream, map.data());
+    if (rc) return rc;
+  }
+  return CUBEEC_OK;
+}
+
 extern "C" int cubeec_dev_verify(cubeec_t* h, int device, const void* d_base, size_t shard_len, size_t shard_pitch,
                                  size_t stripe_pitch, size_t n_stripes, int32_t* d_ok, void* stream) {
   if (!h || !d_ok) return CUBEEC_ERR_INVALID_ARG;
@@ -1224,6 +1319,12 @@ extern "C" int cubeec_dev_verify(cubeec_t* h, int device, const void* d_base, si
   return CUBEEC_OK;
 }
 
+// slot_map (k+m entries, or nullptr = identity): shard i of the code is shard slot_map[i] of the stripe -- the local
+// stripes of the LRC code modes (codemode.GetECLayoutByAZ) reconstruct through it.
+static int dev_reconstruct_core(cubeec_t* h, DevCtx* c, int device, void* d_base, size_t shard_len, size_t shard_pitch,
+                                size_t stripe_pitch, size_t n_stripes, const uint8_t* present, int data_only, void* stream,
+                                const uint8_t* slot_map);
+
 extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, size_t shard_len, size_t shard_pitch,
                                       size_t stripe_pitch, size_t n_stripes, const uint8_t* present, int data_only,
                                       void* stream) {
@@ -1235,22 +1336,41 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
   DevCtx* c = ctx_for_device(device);
   if (!c) return CUBEEC_ERR_INVALID_ARG;
   CU(cudaSetDevice(device));
+  return dev_reconstruct_core(h, c, device, d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, present, data_only, stream, nullptr);
+}
+
+static int dev_reconstruct_core(cubeec_t* h, DevCtx* c, int device, void* d_base, size_t shard_len, size_t shard_pitch,
+                                size_t stripe_pitch, size_t n_stripes, const uint8_t* present, int data_only, void* stream,
+                                const uint8_t* slot_map) {
+  int rc = CUBEEC_OK;
   const int n = h->k + h->m;
+  const std::vector<uint8_t> smap = slot_map ? std::vector<uint8_t>(slot_map, slot_map + n) : std::vector<uint8_t>();
   // plan lookup (same presence array as an earlier call on this device?)
   cubeec::Plan* plan = nullptr;
   {
     std::lock_guard<std::mutex> lk(h->mu);
     for (auto& pl : h->plans)
       if (pl->device == device && pl->data_only == (data_only != 0) && pl->present.size() == n_stripes * (size_t)n &&
-          std::memcmp(pl->present.data(), present, pl->present.size()) == 0) {
+          pl->slot_map == smap && std::memcmp(pl->present.data(), present, pl->present.size()) == 0) {
         plan = pl.get();
         break;
       }
   }
-  // The bit-sliced syndrome kernel is exact but (as measured, profiles/) still slower than the
-  // fixed-arity table kernel on B200; it is opt-in (cubeec_debug_force_kernel(2)) until it wins.
-  const bool use_rec = h->bs_passes == 1 && bs_rec_supported(h->k, h->m) && g_force_kernel.load() == 2 &&
-                       bs_layout_ok((const uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch);
+  // Kernel choice.  One pattern for the whole batch -> the run-time compiled kernel of that pattern (jit.cu), below.
+  // Mixed patterns -> the table kernels.  A/B: 9 = flat-split bit-sliced syndrome kernel (bitslice_syn.cu), 2 = the round-1
+  // syndrome kernel, 1 / 3 = table kernels for everything.
+  const int fkr = g_force_kernel.load();
+  static const bool jit_off = getenv("CUBEEC_NO_JIT") != nullptr;
+  bool single = true;
+  for (size_t s = 1; s < n_stripes && single; s++)
+    for (int i = 0; i < n; i++)
+      if ((present[s * n + i] != 0) != (present[i] != 0)) { single = false; break; }
+  const bool jit_ok = single && !jit_off && fkr != 1 && fkr != 3 && fkr != 4 && fkr != 2 && fkr != 9 && jit_available();
+  const bool layout32 = bs_layout_ok((const uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch);
+  const bool use_old_rec = fkr == 2 && !slot_map && h->bs_passes == 1 && bs_rec_supported(h->k, h->m) && layout32;
+  // (the flat-split syndrome kernel is measured at 0.45 of HBM on C3 against 0.65 for the table kernel: opt-in, force 9)
+  const bool use_syn = fkr == 9 && !slot_map && h->bs_passes == 1 && bs_syn_supported(h->k, h->m) && layout32;
+  const bool use_rec = use_old_rec || use_syn;
   if (plan && use_rec != (plan->d_rec != nullptr)) plan = nullptr;
   std::unique_ptr<cubeec::Plan> fresh;
   if (!plan && use_rec) {
@@ -1302,9 +1422,17 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
     rp.patterns = plan->d_rec;
     rp.pattern_of_stripe = plan->d_pos;
     rp.gf = c->d_gf;
-    CU(launch_bs_rec(h->k, h->m, rp, gm.grid, st2));
+    if (use_syn) {
+      rp.units_per_shard = bs_syn_units_per_shard(shard_len);
+      rp.total_units = (uint64_t)n_stripes * rp.units_per_shard;
+      const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((rp.total_units + 15) / 16, (uint64_t)c->sm_count));
+      CU(launch_bs_syn(h->k, h->m, rp, grid, st2));
+      t_last_kernel = "rs_bssyn_kernel";
+    } else {
+      CU(launch_bs_rec(h->k, h->m, rp, gm.grid, st2));
+      t_last_kernel = "rs_bsrec_kernel";
+    }
     g_launches++;
-    t_last_kernel = "rs_bsrec_kernel";
     if (fresh) {
       std::lock_guard<std::mutex> lk(h->mu);
       if (h->plans.size() < 16) {
@@ -1361,6 +1489,11 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
       for (size_t q = 0; q < n_pat; q++)
         if (j < pat_passes[q].size()) {
           flat[j * n_pat + q] = pat_passes[q][j];
+          if (slot_map) {
+            Pattern& fp = flat[j * n_pat + q];
+            for (int ci = 0; ci < fp.n_in; ci++) fp.in_slot[ci] = slot_map[fp.in_slot[ci]];
+            for (int ri = 0; ri < fp.n_out; ri++) fp.out_slot[ri] = slot_map[fp.out_slot[ri]];
+          }
           fresh->nin[j] = std::max<int>(fresh->nin[j], pat_passes[q][j].n_in);
         }
     CU(cudaMalloc(&fresh->d_pat, flat.size() * sizeof(Pattern)));
@@ -1368,14 +1501,12 @@ extern "C" int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, siz
     CU(cudaMemcpy(fresh->d_pat, flat.data(), flat.size() * sizeof(Pattern), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(fresh->d_pos, pos.data(), n_stripes * sizeof(uint32_t), cudaMemcpyHostToDevice));
     fresh->h_pat = flat;
+    fresh->slot_map = smap;
     plan = fresh.get();
   }
   // One erasure pattern for the whole batch (a repair task: one broken vuid, worker_slice_recover.go:822-871):
   // run the kernel compiled for exactly these decode rows (jit.cu); ~1 s once per pattern, cached.
-  static const bool jit_env_off = getenv("CUBEEC_NO_JIT") != nullptr;
-  const int fk = g_force_kernel.load();
-  if (plan->n_pat == 1 && !jit_env_off && fk != 1 && fk != 3 && fk != 4 &&
-      bs_layout_ok((const uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch)) {
+  if (plan->n_pat == 1 && jit_ok && layout32) {
     if (plan->jit_state == 0) {
       std::vector<const void*> ks;
       bool ok = true;

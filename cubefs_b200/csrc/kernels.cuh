@@ -274,6 +274,9 @@ struct BsRecParams {
   const RecPattern* patterns;
   const uint32_t* pattern_of_stripe;
   const GfDeviceTables* gf;
+  // flat split of the second-generation kernel (bitslice_syn.cu): units of 1 KiB of every shard of a stripe
+  uint32_t units_per_shard;
+  uint64_t total_units;
 };
 
 // Number of bit-sliced passes RS(k, m) with these parity rows takes: 1 (m <= 4); for the generated
@@ -283,6 +286,9 @@ int bs_passes(int k, int m, const uint8_t* parity_rows, int plan);
 int bs_mp_passes(int k, int m, const uint8_t* parity_rows, int plan);           // bitslice_mp.cu
 bool bs_mp_pass_rows(int k, int m, int plan, int pass, int* r0, int* rows);     // m > 4 codes: rows of a pass
 bool bs_rec_supported(int k, int m);
+bool bs_syn_supported(int k, int m);                                             // bitslice_syn.cu
+uint32_t bs_syn_units_per_shard(size_t shard_len);
+cudaError_t launch_bs_syn(int k, int m, const BsRecParams& p, int grid, cudaStream_t st);
 cudaError_t launch_bs_rec(int k, int m, const BsRecParams& p, int grid, cudaStream_t st);
 // crc: 0 none, 1 all shards (pass 0), 2 the pass's outputs only (pass > 0)
 cudaError_t launch_bs(int k, int m, int pass, const BsParams& p, int crc, bool verify, int grid, cudaStream_t st);

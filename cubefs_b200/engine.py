@@ -70,6 +70,9 @@ def load() -> C.CDLL:
     L.cubeec_lrc_encode_contig.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, C.c_int]
     L.cubeec_dev_lrc_encode.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp,
                                         C.c_int, vp]
+    L.cubeec_dev_lrc_verify.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp]
+    L.cubeec_dev_lrc_reconstruct.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp,
+                                             C.c_int, vp]
     L.cubeec_dev_reconstruct.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp, C.c_int, vp]
     L.cubeec_dev_verify.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp]
     L.cubeec_crc32.argtypes = [vp, C.c_size_t, C.c_int, u32p]
@@ -136,6 +139,22 @@ def dev_lrc_encode(global_eng: "RSEngine", local_eng: "RSEngine", az_count: int,
                    device: int = 0):
     _check(load().cubeec_dev_lrc_encode(global_eng._h, local_eng._h, az_count, device, d_base, shard_len, shard_pitch,
                                         stripe_pitch, n_stripes, d_crc or None, poly, stream or None))
+
+
+def dev_lrc_verify(global_eng: "RSEngine", local_eng: "RSEngine", az_count: int, d_base: int, shard_len: int, shard_pitch: int,
+                   stripe_pitch: int, n_stripes: int, d_ok: int, stream: int = 0, device: int = 0):
+    """lrcEncoder.Verify on device-resident LRC stripes: d_ok[s] = 1 iff global and every local parity match."""
+    _check(load().cubeec_dev_lrc_verify(global_eng._h, local_eng._h, az_count, device, d_base, shard_len, shard_pitch, stripe_pitch,
+                                        n_stripes, d_ok, stream or None))
+
+
+def dev_lrc_reconstruct(global_eng: "RSEngine", local_eng: "RSEngine", az_count: int, d_base: int, shard_len: int, shard_pitch: int,
+                        stripe_pitch: int, n_stripes: int, present: np.ndarray, data_only: bool = False, stream: int = 0,
+                        device: int = 0):
+    """lrcEncoder.Reconstruct / ReconstructData on device-resident LRC stripes (present: n_stripes x (N+M+L))."""
+    present = np.ascontiguousarray(present, dtype=np.uint8)
+    _check(load().cubeec_dev_lrc_reconstruct(global_eng._h, local_eng._h, az_count, device, d_base, shard_len, shard_pitch,
+                                             stripe_pitch, n_stripes, present.ctypes.data, int(data_only), stream or None))
 
 
 class StripeDesc(C.Structure):

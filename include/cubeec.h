@@ -180,6 +180,19 @@ int cubeec_dev_encode(cubeec_t* h, int device, void* d_base, size_t shard_len, s
 int cubeec_dev_lrc_encode(cubeec_t* global, cubeec_t* local, int az_count, int device, void* d_base,
                           size_t shard_len, size_t shard_pitch, size_t stripe_pitch, size_t n_stripes,
                           uint32_t* d_crc_out, int crc_poly, void* stream);
+/* lrcEncoder.Verify / Reconstruct / ReconstructData (BS/common/ec/lrcencoder.go:87-200) on device-resident LRC stripes
+ * (N+M+L shards at shard_pitch, a multiple of 32): the global code over the first N+M shards plus one local code per AZ
+ * over codemode.GetECLayoutByAZ's shard list, without leaving HBM between the codes.
+ * verify: d_ok[s] = 1 iff the global parity AND every AZ's local parity of stripe s match.
+ * reconstruct: present = HOST array n_stripes*(N+M+L); global shards come from the global code only (as the reference:
+ * local parity never helps the global decode), missing local parity is rebuilt from its AZ afterwards; data_only =
+ * ReconstructData (global data shards only).  CUBEEC_ERR_UNSUPPORTED: a code without generated network (verify). */
+int cubeec_dev_lrc_verify(cubeec_t* global, cubeec_t* local, int az_count, int device, const void* d_base,
+                          size_t shard_len, size_t shard_pitch, size_t stripe_pitch, size_t n_stripes,
+                          int32_t* d_ok, void* stream);
+int cubeec_dev_lrc_reconstruct(cubeec_t* global, cubeec_t* local, int az_count, int device, void* d_base,
+                               size_t shard_len, size_t shard_pitch, size_t stripe_pitch, size_t n_stripes,
+                               const uint8_t* present, int data_only, void* stream);
 /* present: HOST array n_stripes*(k+m).  Regenerates every missing shard of every stripe in
  * one fused pass (missing parity is produced directly from the survivors). */
 int cubeec_dev_reconstruct(cubeec_t* h, int device, void* d_base, size_t shard_len, size_t shard_pitch,
@@ -242,7 +255,8 @@ const char* cubeec_last_kernel(void);
  * 6 = rolled-loop fused encode+CRC kernel (smaller hot loop; RS(12,4), (10,4), (6,2)),
  * 7 = tile-split fused kernel rs_bs_kernel<crc> for every shard size (default: the flat-split rs_bsf_kernel from
  * 16 KiB), 1000+T = flat-split fused kernel with T threads per CTA (RS(12,4) only),
- * 4 = no run-time compiled (NVRTC) reconstruct kernels: single-pattern batches take the table kernels too. */
+ * 4 = no run-time compiled (NVRTC) reconstruct kernels: single-pattern batches take the table kernels too,
+ * 9 = flat-split bit-sliced syndrome kernel (rs_bssyn_kernel) for cubeec_dev_reconstruct. */
 void cubeec_debug_force_kernel(int which);
 /* Tests: generate and NVRTC-compile (no device needed) the run-time specialised reconstruct kernel of RS(k, m) for
  * a presence pattern.  0 = compiled, 101 = NVRTC not installed, 102 = compile error (log), else CUBEEC_ERR_*. */

@@ -161,3 +161,110 @@ def test_single_pattern_reconstruct_runtime_compiled_kernel(cb, oracle, case):
     for i in range(n):
         if i not in miss:
             assert np.array_equal(outs[0][:, i, :], host[:, i, :])
+
+
+@pytest.mark.parametrize("km", [(12, 4), (6, 3), (4, 2), (20, 4), (10, 4), (3, 3), (8, 4)])
+def test_mixed_pattern_reconstruct_syndrome_kernel_v2(cb, oracle, km):
+    """Batches that mix erasure patterns (config C3) through the opt-in flat-split syndrome kernel (bitslice_syn.cu, force 9): every count of
+    missing data / parity shards up to m, ragged and multi-unit sizes, warps whose runs cross stripe (= pattern)
+    boundaries.  Bit-exact against the originals and against the table kernels (force 8); data_only leaves parity alone."""
+    import torch
+    k, m = km
+    n = k + m
+    ora = oracle.RS(k, m)
+    eng = cb.RSEngine(k, m)
+    rng = np.random.default_rng(k * 31 + m)
+    for S, ns in ((349526 if k == 12 else 70001, 37), (1024 * 3, 300), (33, 64), (2048 + 6, 200)):
+        P = (S + 127) // 128 * 128
+        host = rng.integers(0, 256, (ns, n, P), dtype=np.uint8)
+        for s in range(ns):
+            ora.encode([host[s, i, :S] for i in range(n)])
+        present = np.ones((ns, n), dtype=np.uint8)
+        for s in range(ns):
+            e = int(rng.integers(0, m + 1))                    # 0 .. m erasures, anywhere
+            present[s, rng.choice(n, size=e, replace=False)] = 0
+        for data_only in (False, True):
+            outs = []
+            for force in (9, 8):
+                cb.force_kernel(force)
+                try:
+                    broken = host.copy()
+                    for s in range(ns):
+                        broken[s, present[s] == 0, :] = 0xC3
+                    dev = torch.from_numpy(broken).cuda()
+                    eng.dev_reconstruct(dev.data_ptr(), S, P, n * P, ns, present, data_only=data_only)
+                    name = cb.last_kernel()
+                    torch.cuda.synchronize()
+                    outs.append(dev.cpu().numpy())
+                finally:
+                    cb.force_kernel(0)
+                assert name == ("rs_bssyn_kernel" if force == 9 else name), name
+                if force == 8:
+                    assert name in ("rs_tabk_kernel", "rs_tab_kernel"), name
+            for s in range(ns):
+                for i in range(n):
+                    regenerated = present[s, i] == 0 and not (data_only and i >= k)
+                    want = host[s, i, :S] if (present[s, i] or regenerated) else None
+                    if want is not None:
+                        assert np.array_equal(outs[0][s, i, :S], want), (km, S, s, i, data_only)
+                        assert np.array_equal(outs[1][s, i, :S], want), (km, S, s, i, data_only)
+
+
+@pytest.mark.parametrize("mode", [(6, 10, 2, 2), (16, 20, 2, 2), (6, 3, 3, 3), (4, 4, 2, 2)])
+def test_lrc_verify_and_reconstruct_on_device(cb, oracle, mode):
+    """lrcEncoder.Verify / Reconstruct / ReconstructData (lrcencoder.go:87-200) on device-resident LRC stripes: global
+    code + per-AZ local codes through slot maps, against the oracle's composition of the same codes."""
+    import torch
+    N, M, L, az = mode
+    n, ng = N + M + L, N + M
+    kl, ml = ng // az, L // az
+    ge, le = cb.RSEngine(N, M), cb.RSEngine(kl, ml)
+    S, ns = 20000 + 6, 40
+    P = (S + 127) // 128 * 128
+    rng = np.random.default_rng(N * 100 + M)
+    host = rng.integers(0, 256, (ns, n, P), dtype=np.uint8)
+    og, ol = oracle.RS(N, M), oracle.RS(kl, ml)
+    for s in range(ns):
+        og.encode([host[s, i, :S] for i in range(ng)])
+        for a in range(az):
+            members = list(range(a * N // az, (a + 1) * N // az)) + list(range(N + a * M // az, N + (a + 1) * M // az))
+            ol.encode([host[s, i, :S] for i in members] + [host[s, ng + a * ml + i, :S] for i in range(ml)])
+    dev = torch.from_numpy(host).cuda()
+    dok = torch.zeros(ns, dtype=torch.int32, device="cuda")
+    # the device encode produces the same stripes (fused LRC path)
+    enc = torch.from_numpy(host).cuda()
+    enc[:, N:, :] = 0
+    cb.dev_lrc_encode(ge, le, az, enc.data_ptr(), S, P, n * P, ns)
+    torch.cuda.synchronize()
+    assert torch.equal(enc[:, :, :S], dev[:, :, :S])
+    cb.dev_lrc_verify(ge, le, az, dev.data_ptr(), S, P, n * P, ns, dok.data_ptr())
+    assert dok.cpu().numpy().tolist() == [1] * ns
+    # one flipped bit: in a global parity shard of stripe 3, in a local parity shard of stripe 7, in data of stripe 11
+    dev[3, N + 1, 5] ^= 1
+    dev[7, ng + L - 1, S - 1] ^= 0x80
+    dev[11, 0, 100] ^= 4
+    cb.dev_lrc_verify(ge, le, az, dev.data_ptr(), S, P, n * P, ns, dok.data_ptr())
+    want = [1] * ns
+    want[3] = want[7] = want[11] = 0
+    assert dok.cpu().numpy().tolist() == want
+    # reconstruct: per stripe a random set of missing global shards (<= M) and missing local parity
+    present = np.ones((ns, n), dtype=np.uint8)
+    for s in range(ns):
+        e = int(rng.integers(0, min(M, 4) + 1))
+        present[s, rng.choice(ng, size=e, replace=False)] = 0
+        if s % 3 == 0:
+            present[s, ng + int(rng.integers(0, L))] = 0
+    for data_only in (False, True):
+        broken = host.copy()
+        for s in range(ns):
+            broken[s, present[s] == 0, :] = 0x3C
+        dev = torch.from_numpy(broken).cuda()
+        cb.dev_lrc_reconstruct(ge, le, az, dev.data_ptr(), S, P, n * P, ns, present, data_only=data_only)
+        torch.cuda.synchronize()
+        out = dev.cpu().numpy()
+        for s in range(ns):
+            for i in range(n):
+                if present[s, i] or (not data_only) or i < N:
+                    assert np.array_equal(out[s, i, :S], host[s, i, :S]), (mode, s, i, data_only)
+                else:
+                    assert np.array_equal(out[s, i, :S], broken[s, i, :S]), (mode, s, i, "left missing")

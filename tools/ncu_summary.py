@@ -57,3 +57,25 @@ for r in rows[2:]:
 print(f"dynamic SASS mix ({tot} warp instructions, {len(rows) - 2} static):")
 for op, n in mix.most_common(12):
     print(f"   {op:12s} {100.0 * n / tot:5.1f} %")
+
+# ---- where the warps wait: SASS instructions with the most stall samples of the top reasons ----
+try:
+    cols = {h: i for i, h in enumerate(h2)}
+    print("source page columns:", [h for h in h2][:60])
+    samp = cols.get("# Samples") or cols.get("Warp Stall Sampling (All Samples)") or cols.get("Samples")
+    stall_cols = [(h, i) for h, i in cols.items() if h.startswith("stall_") or "stall" in h.lower()]
+    addr = cols.get("Address")
+    if samp is not None:
+        scored = []
+        for k, r in enumerate(rows[2:]):
+            try:
+                scored.append((int(r[samp]), k, r))
+            except (ValueError, IndexError):
+                pass
+        tot_s = sum(x[0] for x in scored) or 1
+        print(f"top SASS instructions by stall samples ({tot_s} samples; columns: {[h for h, _ in stall_cols][:12]}):")
+        for n_s, k, r in sorted(scored, reverse=True)[:30]:
+            detail = " ".join(f"{h.replace('stall_', '')}={r[i]}" for h, i in stall_cols if i < len(r) and r[i] not in ("0", "", "0.00"))
+            print(f"   #{k:5d} {100.0 * n_s / tot_s:5.2f}%  {r[si].strip()[:70]:70s} {detail[:150]}")
+except Exception as e:   # noqa: BLE001
+    print("stall attribution unavailable:", e)
