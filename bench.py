@@ -49,8 +49,8 @@ def shard_size(blob, k, min_shard=2048):
 
 
 PROFILE_OF_KERNEL = {"rs_bsf_kernel<crc>": "r02_prof_bsf_crc.txt", "rs_bs_kernel<crc>": "r01_prof_r1_bs_crc.txt",
-                     "rs_bs_kernel": "r02_prof_bs_nocrc.txt", "rs_tabk_kernel": "r01_prof_tabk_rec.txt",
-                     "rs_bsg_kernel": "r02_prof_bsg_rec.txt"}
+                     "rs_bs_kernel": "r02_prof_bs_nocrc.txt", "rs_tabk_kernel": "r02_prof_tabk_rec.txt",
+                     "rs_jit_kernel": "r02_prof_jit_rec.txt"}
 
 
 def traffic_from_profile(kernel: str, stripes: int):

@@ -37,9 +37,6 @@ cudaError_t launch_bsf(int k, int m, int pass, int crc_mode, const BsfParams& p,
 cudaError_t launch_bsf_variant(int threads, const BsfParams& p, int grid, cudaStream_t st) {
   switch (threads) {
     case 512: return bsf_launch_one<12, 4, 0, 1, 512>(p, grid, st);
-    case 448: return bsf_launch_mr<448, 4, 144>(p, grid, st);
-    case 416: return bsf_launch_mr<416, 4, 152>(p, grid, st);
-    case 480: return bsf_launch_mr<480, 3, 136>(p, grid, st);
     case 384: return bsf_launch_one<12, 4, 0, 1, 384>(p, grid, st);
     case 320: return bsf_launch_one<12, 4, 0, 1, 320>(p, grid, st);
     case 256: return bsf_launch_one<12, 4, 0, 1, 256>(p, grid, st);

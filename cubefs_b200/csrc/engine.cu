@@ -624,8 +624,29 @@ bool bs_is_packed(size_t shard_len) {
 
 // Geometry of the bit-sliced kernels; shards shorter than a tile use packed mode (pieces of many
 // stripes share a tile).
-Geometry bs_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes) {
+// balanced = a kernel without per-item cost (plain encode, verify: no CRC alignment per segment): the number of
+// segments per shard is chosen to minimise ceil(items / SMs) * tiles per item, so that e.g. 383 stripes of 11 tiles
+// do not run 11 rounds of 3-tile items (33 tile steps, 86 % of the 28.5 the work needs) but 29 rounds of 1-tile items.
+Geometry bs_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes, bool balanced = false) {
   Geometry gm = pick_geometry(c, shard_len, n_stripes, false, kBsTile);
+  if (balanced && !bs_is_packed(shard_len) && n_stripes > 0) {
+    const uint64_t tiles_total = (shard_len + kBsTile - 1) / kBsTile, sms = (uint64_t)c.sm_count;
+    uint64_t best_seg = gm.n_seg, best_cost = ~0ull;
+    for (uint64_t ns = 1; ns <= tiles_total; ns++) {
+      const uint64_t tps = (tiles_total + ns - 1) / ns, nseg = (tiles_total + tps - 1) / tps;
+      const uint64_t items = n_stripes * nseg;
+      const uint64_t cost = ((items + sms - 1) / sms) * tps * 64 + (items + sms - 1) / sms;   // tile steps (x64) + a little per item
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_seg = nseg;
+      }
+    }
+    const uint64_t tps = (tiles_total + best_seg - 1) / best_seg;
+    gm.n_seg = (uint32_t)((tiles_total + tps - 1) / tps);
+    gm.tiles_per_seg = (uint32_t)tps;
+    gm.tiles_last = (uint32_t)(tiles_total - (uint64_t)(gm.n_seg - 1) * tps);
+    gm.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_stripes * gm.n_seg, sms));
+  }
   if (bs_is_packed(shard_len)) {
     const uint32_t pps = (uint32_t)((shard_len + kBsPiece - 1) / kBsPiece);
     const uint64_t tiles = ((uint64_t)n_stripes * pps + kBsThreads - 1) / kBsThreads;
@@ -707,7 +728,7 @@ struct FlatGeometry {
 
 int bsf_threads() {
   const int f = g_force_kernel.load();
-  return (f >= 1000 && f < 2000) ? f - 1000 : kBsfThreads;   // cubeec_debug_force_kernel(1000 + threads): A/B aid
+  return (f >= 1000 && f < 2000) ? f - 1000 : kBsfThreads;   // cubeec_debug_force_kernel(1000 + variant): A/B aid
 }
 
 FlatGeometry flat_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes) {
@@ -797,7 +818,7 @@ int finalize_flat_crc(cudaStream_t stream, const uint32_t* d_part, size_t n_stri
   f.init_term = P.mul(0xFFFFFFFFu, P.shift_bytes_const((int64_t)shard_len));
   f.out = d_out;
   CU(launch_crc_parts_finalize(f, stream));
-  g_launches++;
+  g_launches += 3;   // zero, scatter, finish
   return CUBEEC_OK;
 }
 
@@ -851,7 +872,7 @@ int dev_encode_impl(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, 
     // bit-sliced XOR-network kernel with the CTA-tile split (bitslice.cu): plain encode, verify, packed mode
     const bool ws = want_crc && g_force_kernel.load() == 5 && h->bs_passes == 1 && bsw_supported(h->k, h->m) &&
                     !bs_is_packed(shard_len);
-    const Geometry gm = ws ? pick_geometry(c, shard_len, n_stripes, false, kBswTile) : bs_geometry(c, shard_len, n_stripes);
+    const Geometry gm = ws ? pick_geometry(c, shard_len, n_stripes, false, kBswTile) : bs_geometry(c, shard_len, n_stripes, !want_crc);
     AsyncScratch scratch(stream);
     if (want_crc && !d_part) {
       CU(scratch.alloc(n_stripes * n * gm.n_seg * sizeof(uint32_t)));
@@ -1232,7 +1253,7 @@ extern "C" int cubeec_dev_lrc_verify(cubeec_t* global, cubeec_t* local, int az_c
     st = lease.lane->stream;
   }
   const int n_slots = y.N + y.M + y.L;
-  const Geometry gm = bs_geometry(*c, shard_len, n_stripes);
+  const Geometry gm = bs_geometry(*c, shard_len, n_stripes, true);
   // d_ok doubles as the mismatch flag array: every code of the stripe raises the same flag, then it is inverted
   CU(cudaMemsetAsync(d_ok, 0, n_stripes * sizeof(int32_t), st));
   rc = bs_run(global, *c, st, (uint8_t*)d_base, shard_len, shard_pitch, stripe_pitch, n_stripes, gm, n_slots, nullptr, y.N, 0, nullptr, 0,

@@ -603,40 +603,54 @@ cudaError_t launch_crc_finalize(const CrcFinalizeParams& p, cudaStream_t stream)
 //   R = sum_j part_j * x^(8 * unit * units after part j);  crc = ~( R * fix ^ 0xFFFFFFFF * x^(8 len) ).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t cpf_run_lo(uint64_t g, uint64_t U, uint64_t GW) { return g * U / GW; }
-__global__ void crc_parts_finalize_kernel(const CrcPartsFinalizeParams p) {
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.n_stripes * p.n_out) return;
-  const uint32_t s = idx / p.n_out, slot = p.first_slot + idx % p.n_out;
+// One thread per (stripe, slot, part): a batch of few, long stripes has hundreds of parts per shard (the number of
+// warp runs that touch it), so the chain is not walked serially -- every part is moved to the end of its shard on its
+// own (x^(8 * unit * units after it), square-and-multiply over the precomputed x_unit_pow table) and XOR-accumulated.
+__global__ void crc_parts_scatter_kernel(const CrcPartsFinalizeParams p) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t total = (uint64_t)p.n_stripes * p.n_out * p.max_parts;
+  if (idx >= total) return;
+  const uint32_t j = (uint32_t)(idx % p.max_parts);
+  const uint64_t sq = idx / p.max_parts;
+  const uint32_t s = (uint32_t)(sq / p.n_out), slot = p.first_slot + (uint32_t)(sq % p.n_out);
   const uint64_t U = p.total_units, GW = p.total_warps, wt = p.units_per_shard;
   const uint64_t u0 = (uint64_t)s * wt, u1 = u0 + wt;
   uint64_t g = u0 * GW / U;
   while (g + 1 < GW && cpf_run_lo(g + 1, U, GW) <= u0) g++;
   while (g > 0 && cpf_run_lo(g, U, GW) > u0) g--;
-  const uint32_t* part = p.crc_part + ((size_t)s * p.n_slots + slot) * p.max_parts;
-  uint32_t r = 0;
-  for (uint32_t j = 0; j < p.max_parts; j++, g++) {
-    uint64_t a = cpf_run_lo(g, U, GW), b = cpf_run_lo(g + 1, U, GW);
-    if (a < u0) a = u0;
-    if (b > u1) b = u1;
-    if (a >= b) {
-      if (a >= u1) break;
-      continue;   // an empty run (more warps than units)
-    }
-    // r = r * x^(8 * unit * (b - a)) ^ part
-    uint64_t n = b - a;
-    for (int i = 0; n; i++, n >>= 1)
-      if (n & 1) r = gf32_mul(r, p.x_unit_pow[i], p.poly);
-    r ^= part[j];
-    if (b >= u1) break;
-  }
-  r = gf32_mul(r, p.fix, p.poly);
-  p.out[(size_t)s * p.n_slots + slot] = ~(r ^ p.init_term);
+  g += j;   // part j of the stripe belongs to run (first owner + j)
+  if (g >= GW) return;
+  uint64_t a = cpf_run_lo(g, U, GW), b = cpf_run_lo(g + 1, U, GW);
+  if (a < u0) a = u0;
+  if (b > u1) b = u1;
+  if (a >= b) return;   // an empty run, or a run beyond this stripe
+  uint32_t r = p.crc_part[((size_t)s * p.n_slots + slot) * p.max_parts + j];
+  uint64_t n = u1 - b;   // units behind this part
+  for (int i = 0; n; i++, n >>= 1)
+    if (n & 1) r = gf32_mul(r, p.x_unit_pow[i], p.poly);
+  atomicXor(&p.out[(size_t)s * p.n_slots + slot], r);
+}
+// crc = ~( R * fix ^ 0xFFFFFFFF * x^(8 len) )
+__global__ void crc_parts_finish_kernel(const CrcPartsFinalizeParams p) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.n_stripes * p.n_out) return;
+  const uint32_t s = idx / p.n_out, slot = p.first_slot + idx % p.n_out;
+  uint32_t* o = p.out + (size_t)s * p.n_slots + slot;
+  *o = ~(gf32_mul(*o, p.fix, p.poly) ^ p.init_term);
+}
+__global__ void crc_parts_zero_kernel(const CrcPartsFinalizeParams p) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.n_stripes * p.n_out) return;
+  p.out[(size_t)(idx / p.n_out) * p.n_slots + p.first_slot + idx % p.n_out] = 0;
 }
 
 cudaError_t launch_crc_parts_finalize(const CrcPartsFinalizeParams& p, cudaStream_t stream) {
   const int nt = 128;
   const uint32_t n = p.n_stripes * p.n_out;
-  crc_parts_finalize_kernel<<<(n + nt - 1) / nt, nt, 0, stream>>>(p);
+  const uint64_t total = (uint64_t)n * p.max_parts;
+  crc_parts_zero_kernel<<<(n + nt - 1) / nt, nt, 0, stream>>>(p);
+  crc_parts_scatter_kernel<<<(unsigned)((total + nt - 1) / nt), nt, 0, stream>>>(p);
+  crc_parts_finish_kernel<<<(n + nt - 1) / nt, nt, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
