@@ -16,9 +16,9 @@
 // Why a second generation (profiles/r02_prof_bsrec.txt, the round-1 kernel at 0.49 of HBM): issue slots 38 % busy,
 // long_scoreboard 5.7 warps per issue, DRAM 40 % busy -- its conditional loads were not running ahead of the coding, and
 // every stripe cost a CTA-wide barrier + table rebuild.  Here: flat split (a warp owns a contiguous run of 1 KiB units,
-// no barrier in the main loop), a 4-deep load ring indexed by shard slot whose loads are issued three slots ahead
-// (and for the next unit before the solve stage of this one), and solve tables private to the warp (2 copies, rebuilt
-// by the warp alone when its stripe changes).
+// no barrier in the main loop), shards staged in shared memory by cp.async three slots ahead (and for the next unit
+// before the solve stage of this one) with counted waits, and solve tables private to the warp (2 copies, rebuilt by the
+// warp alone when its stripe changes).
 #include <type_traits>
 
 #include "bs_net_gen.cuh"
@@ -33,9 +33,26 @@ namespace {
 
 constexpr int kSynThreads = 512;
 constexpr int kSynUnit = 1024;                 // bytes of a shard per unit: one 32-byte column per lane
-constexpr int kSynRing = 4;
+constexpr int kSynRing = 4;                    // staged shards per thread (power of two)
 constexpr int kSynTabBytes = 4 * 256 * 2 * 4;  // per warp: [4 syndromes][256][2 copies] u32
-constexpr size_t kSynSmemBytes = 1024 + (size_t)(kSynThreads / 32) * kSynTabBytes;
+constexpr size_t kSynStageBytes = (size_t)kSynRing * 2 * kSynThreads * 16;   // [slot][16-byte half][thread]
+constexpr size_t kSynSmemBytes = 1024 + (size_t)(kSynThreads / 32) * kSynTabBytes + kSynStageBytes;
+
+// The loads of the ring do not go through registers: ptxas puts every 256-bit LDG of the ring on ONE scoreboard and
+// the first use of the oldest load then also waits for the load issued a few instructions earlier (decoded from the
+// SASS control words; profiles/r02_prof_bssyn_ring4.txt: 46 % of all warp samples sit on those first uses).  cp.async
+// (LDGSTS) copies global -> shared without a register scoreboard, and cp.async.wait_group N is a COUNTED wait: "all
+// but the N youngest groups have landed" -- exactly the semantics a software pipeline needs.  Every thread copies and
+// later reads only its own 32 bytes, so no barrier is involved.
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+}
 
 template <int I, int N>
 struct SFor {
@@ -67,11 +84,11 @@ __global__ void __launch_bounds__(kSynThreads, 1) rs_bssyn_kernel(const BsRecPar
   const uint32_t wt = p.units_per_shard;
   uint32_t s = (uint32_t)(u_lo / wt), t = (uint32_t)(u_lo - (uint64_t)s * wt);
 
-  uint32_t ring[RD][8];
-#pragma unroll
-  for (int b = 0; b < RD; b++)
-#pragma unroll
-    for (int i = 0; i < 8; i++) ring[b][i] = 0;
+  static_assert((RD & (RD - 1)) == 0, "ring size must be a power of two");
+  // staging area of this thread: slot r, half h at stage_base + ((r * 2 + h) * threads + tid) * 16
+  const uint32_t stage_base = smem_addr(smem + 1024 + (size_t)NW * kSynTabBytes) + (uint32_t)tid * 16u;
+  auto stage_addr = [&](uint32_t r, uint32_t h) -> uint32_t { return stage_base + ((r * 2u + h) * (uint32_t)kSynThreads) * 16u; };
+  uint32_t rbase = 0;   // ring position of slot 0 of the current unit (advances by N per unit, modulo RD)
 
   // pattern of the current stripe (warp-uniform values)
   uint32_t cur_pat = 0xFFFFFFFFu, want = 0, syn_mask = 0, t_mask = 0, n_out = 0, out_slots = 0, out_prows = 0;
@@ -133,10 +150,19 @@ __global__ void __launch_bounds__(kSynThreads, 1) rs_bssyn_kernel(const BsRecPar
       const uint32_t ncol = t2 * kSynUnit + (uint32_t)lane * 32u;
       const uint8_t* nsrc = p.base + (size_t)s2 * p.stripe_pitch + ncol;
       const bool nlive = next_same && ncol < p.shard_len;
+      // issue(c, base, live): copy slot c of the unit at `base` into its ring position, as its own cp.async group
+      auto issue = [&](const int c, const uint8_t* base, const bool on, const uint32_t rb) {
+        if (((want >> c) & 1u) && on) {
+          const uint8_t* g = base + (size_t)c * p.shard_pitch;
+          const uint32_t r = (rb + (uint32_t)c) & (RD - 1);
+          cp_async16(stage_addr(r, 0), g);
+          cp_async16(stage_addr(r, 1), g + 16);
+        }
+        cp_async_commit();   // a group per slot, empty or not: the wait below counts groups
+      };
       if (!primed) {
 #pragma unroll
-        for (int c = 0; c < RD - 1; c++)
-          if (((want >> c) & 1u) && live) ldg256(src + (size_t)c * p.shard_pitch, ring[c]);
+        for (int c = 0; c < RD - 1; c++) issue(c, src, live, rbase);
       }
       uint32_t acc[8 * M];
 #pragma unroll
@@ -145,14 +171,15 @@ __global__ void __launch_bounds__(kSynThreads, 1) rs_bssyn_kernel(const BsRecPar
 
       SFor<0, N>::run([&](auto cc) {
         constexpr int c = decltype(cc)::value;
-        // load RD-1 slots ahead; past the last slot: slots 0 .. RD-2 of the next unit
-        if constexpr (c + RD - 1 < N) {
-          if (((want >> (c + RD - 1)) & 1u) && live) ldg256(src + (size_t)(c + RD - 1) * p.shard_pitch, ring[(c + RD - 1) % RD]);
-        } else {
-          if (((want >> (c + RD - 1 - N)) & 1u) && nlive) ldg256(nsrc + (size_t)(c + RD - 1 - N) * p.shard_pitch, ring[(c + RD - 1) % RD]);
-        }
-        if ((want >> c) & 1u) {   // warp-uniform
-          uint32_t (&w)[8] = ring[c % RD];
+        // copy RD-1 slots ahead; past the last slot: slots 0 .. RD-2 of the next unit
+        if constexpr (c + RD - 1 < N) issue(c + RD - 1, src, live, rbase);
+        else issue(c + RD - 1 - N, nsrc, nlive, rbase + (uint32_t)N);
+        cp_async_wait<RD - 1>();   // everything but the RD-1 youngest groups has landed: slot c is in shared memory
+        if ((want >> c) & 1u) {    // warp-uniform
+          uint32_t w[8];
+          const uint32_t r = (rbase + (uint32_t)c) & (RD - 1);
+          lds128(stage_addr(r, 0), w[0], w[1], w[2], w[3]);
+          lds128(stage_addr(r, 1), w[4], w[5], w[6], w[7]);
           if (!full) {
 #pragma unroll
             for (int i = 0; i < 8; i++) w[i] &= msk[i];
@@ -166,18 +193,7 @@ __global__ void __launch_bounds__(kSynThreads, 1) rs_bssyn_kernel(const BsRecPar
           }
         }
       });
-      if constexpr (N % RD != 0) {
-        // the next unit's slots j < RD-1 sit in ring[(N + j) % RD]: move them to ring[j]
-        uint32_t mv[RD - 1][8];
-#pragma unroll
-        for (int j = 0; j < RD - 1; j++)
-#pragma unroll
-          for (int i = 0; i < 8; i++) mv[j][i] = ring[(N + j) % RD][i];
-#pragma unroll
-        for (int j = 0; j < RD - 1; j++)
-#pragma unroll
-          for (int i = 0; i < 8; i++) ring[j][i] = mv[j][i];
-      }
+      rbase = (rbase + (uint32_t)N) & (RD - 1);
       primed = next_same;
 
       // back to bytes, in place, for the rows that are used (syndromes and T_p of missing parity)
@@ -239,6 +255,7 @@ __global__ void __launch_bounds__(kSynThreads, 1) rs_bssyn_kernel(const BsRecPar
     else {
       primed = false;
     }
+    if (!primed) cp_async_wait<0>();   // nothing of this warp stays in flight across a pattern change / the end of its run
     s = s2;
     t = t2;
   }

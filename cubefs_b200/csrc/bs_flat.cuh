@@ -79,13 +79,17 @@ __host__ __device__ __forceinline__ uint64_t bsf_owner(uint64_t u, uint64_t U, u
 // RD = number of 256-bit load buffers (RD - 1 shards in flight ahead of the one being coded).
 // PF: also prefetch into L2 (no registers) shard c of the NEXT column while shard c of this one is coded, so that the
 // 256-bit loads of the ring find their lines in L2.  Measured (B200, C2): 0.519 with, 0.535 without -- off.
+// A variant that staged the data shards through shared memory with cp.async (counted waits, no LDG scoreboards: ptxas puts
+// the ring's LDGs on scoreboards 2-5 and the CRC lookups on 0-4, so lookup waits can inherit DRAM latency) was measured at
+// 0.48-0.49 (384 threads, 4 / 6 slots) and 0.505 (512 threads x 128 registers) against 0.536: the extra shared-memory
+// traffic costs more than the aliasing.  Not kept.
 // (Warp counts between 12 and 16 do not exist for this kernel: registers are per scheduler, 16 K each, so 4 warps per
 // scheduler cap a thread at 128 registers and 3 at 168; ptxas picks exactly those two.)
 template <int K, int M, int V, int CRC, int NT, int RD, bool PF = false>
 __device__ __forceinline__ void bsf_body(const BsfParams& p) {
   static_assert(CRC == 1 || CRC == 2, "fused-CRC kernel");
   static_assert(K >= 2 && K + M <= 32, "lane q publishes the remainder of shard q");
-  static_assert(RD >= 3 && K >= RD - 1, "load ring");
+  static_assert(RD >= 2 && K >= RD - 1, "load ring");
   using Net = BsNet<K, M, V>;
   constexpr int C0 = CRC == 2 ? K : 0;   // first checksummed shard (local index)
   constexpr int NW = NT / 32;
