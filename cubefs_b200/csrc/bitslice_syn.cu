@@ -94,8 +94,12 @@ __global__ void __launch_bounds__(kSynThreads, 1) rs_bssyn_kernel(const BsRecPar
   uint32_t cur_pat = 0xFFFFFFFFu, want = 0, syn_mask = 0, t_mask = 0, n_out = 0, out_slots = 0, out_prows = 0;
   bool primed = false;   // ring[0 .. RD-2] already hold (or are receiving) slots 0 .. RD-2 of this unit
 
+  uint32_t pat_id = 0, pat_s = 0xFFFFFFFFu;
   for (uint64_t u = u_lo; u < u_hi; u++) {
-    const uint32_t pat_id = p.pattern_of_stripe ? p.pattern_of_stripe[s] : 0u;
+    if (s != pat_s) {   // one (dependent) global load per stripe, not per unit
+      pat_s = s;
+      pat_id = p.pattern_of_stripe ? p.pattern_of_stripe[s] : 0u;
+    }
     if (pat_id != cur_pat) {
       cur_pat = pat_id;
       primed = false;

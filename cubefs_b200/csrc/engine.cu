@@ -1641,6 +1641,9 @@ struct CoBatch {
   size_t S = 0, P = 0;
   int n = 0, poly = 0;
   bool want_crc = false;
+  int op = 0;                   // 0 = encode, 1 = reconstruct
+  bool data_only = false;       // reconstruct: ReconstructData
+  std::vector<uint8_t> present; // reconstruct: [cap][n] presence flags of the slots
   int cap = 0, claimed = 0, filled = 0, left = 0;   // left: callers that still have to copy their results out
   enum { OPEN, CLOSED, RUNNING, DONE } state = OPEN;
   std::chrono::steady_clock::time_point deadline;
@@ -1668,7 +1671,42 @@ std::atomic<int> g_co_max_batch{32};
 std::atomic<int> g_co_delay_us{100};
 CoQueue g_co;   // device 0 of the engine (the single-stripe host calls always use the first configured device)
 
+// a reconstruct batch: survivors in (runs of consecutive shards merged into one copy), one batched device reconstruct
+// (one pattern for all slots -> the run-time compiled kernel), regenerated shards out
+int co_run_reconstruct(CoBatch& b, DevCtx& c, Lane& l) {
+  const size_t dstripe = b.P * b.n;
+  const int n = b.n, k = b.h->k;
+  int rc = lane_reserve(l, dstripe * b.claimed, 256);
+  if (rc) return rc;
+  CU(cudaSetDevice(c.device));
+  auto copy_runs = [&](bool to_device) -> int {
+    for (int s = 0; s < b.claimed; s++) {
+      const uint8_t* pr = &b.present[(size_t)s * n];
+      for (int i = 0; i < n;) {
+        const bool pick = to_device ? pr[i] != 0 : (pr[i] == 0 && !(b.data_only && i >= k));
+        if (!pick) { i++; continue; }
+        int j = i + 1;
+        while (j < n && (to_device ? pr[j] != 0 : (pr[j] == 0 && !(b.data_only && j >= k)))) j++;
+        uint8_t* hp = b.h_buf + (size_t)s * dstripe + (size_t)i * b.P;
+        uint8_t* dp = l.d_buf + (size_t)s * dstripe + (size_t)i * b.P;
+        if (to_device) CU(cudaMemcpyAsync(dp, hp, (size_t)(j - i) * b.P, cudaMemcpyHostToDevice, l.stream));
+        else CU(cudaMemcpyAsync(hp, dp, (size_t)(j - i) * b.P, cudaMemcpyDeviceToHost, l.stream));
+        i = j;
+      }
+    }
+    return CUBEEC_OK;
+  };
+  if ((rc = copy_runs(true))) return rc;
+  rc = dev_reconstruct_core(b.h, &c, c.device, l.d_buf, b.S, b.P, dstripe, (size_t)b.claimed, b.present.data(), b.data_only ? 1 : 0,
+                            (void*)l.stream, nullptr);
+  if (rc) return rc;
+  if ((rc = copy_runs(false))) return rc;
+  CU(cudaStreamSynchronize(l.stream));
+  return CUBEEC_OK;
+}
+
 int co_run_batch(CoBatch& b, DevCtx& c, Lane& l) {
+  if (b.op == 1) return co_run_reconstruct(b, c, l);
   const size_t dstripe = b.P * b.n;
   const int k = b.h->k, m = b.h->m;
   const size_t part_bytes = b.want_crc ? round_up(crc_part_bytes(c, b.S, (size_t)b.claimed, b.n), 256) : 0;
@@ -1748,96 +1786,142 @@ void co_start_locked(CoQueue& q) {
   });
 }
 
-// cubeec_encode through the queue.  Returns -1 when the call is not eligible (queue off, m == 0, ...).
-int co_encode(cubeec* h, uint8_t* const* shards, size_t S, int n, uint32_t* crc_out, int crc_poly) {
-  const int max_batch = g_co_max_batch.load();
-  if (max_batch <= 1 || h->m == 0) return -1;
-  const size_t P = round_up(S, kAlign);
-  const size_t dstripe = P * n;
-  int cap = (int)std::min<size_t>((size_t)max_batch, std::max<size_t>(1, kCoBatchBytes / dstripe));
-  if (cap <= 1) return -1;   // stripes this large are a batch by themselves
+// Claim a slot in the open batch of the key (handle, shard size, operation, flags), creating the batch if needed.
+// Returns the batch and the slot index; nullptr + rc on failure.
+CoBatch* co_claim(cubeec* h, size_t S, int n, int op, bool want_crc, int crc_poly, bool data_only, int cap, int* idx_out, int* rc_out) {
+  const size_t P = round_up(S, kAlign), dstripe = P * n;
   CoQueue& q = g_co;
   CoBatch* b = nullptr;
-  int idx = 0;
-  {
-    std::unique_lock<std::mutex> lk(q.mu);
-    co_start_locked(q);
-    for (CoBatch* x : q.open)
-      if (x->h == h && x->S == S && x->poly == crc_poly && x->want_crc == (crc_out != nullptr) && x->state == CoBatch::OPEN &&
-          x->claimed < x->cap) {
-        b = x;
-        break;
-      }
-    if (!b) {
-      if (!q.pool.empty()) {
-        b = q.pool.back();
-        q.pool.pop_back();
-      } else {
-        b = new CoBatch();
-      }
-      b->h = h;
-      b->S = S;
-      b->P = P;
-      b->n = n;
-      b->poly = crc_poly;
-      b->want_crc = crc_out != nullptr;
-      b->cap = cap;
-      b->claimed = b->filled = b->left = 0;
-      b->state = CoBatch::OPEN;
-      b->rc = CUBEEC_OK;
-      b->deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(std::max(0, g_co_delay_us.load()));
-      const size_t need = dstripe * (size_t)cap, need_crc = (size_t)cap * n * 4;
-      if (need > b->h_cap || need_crc > b->crc_cap) {
-        lk.unlock();   // pinned allocation is slow: not under the queue lock
+  std::unique_lock<std::mutex> lk(q.mu);
+  co_start_locked(q);
+  for (CoBatch* x : q.open)
+    if (x->h == h && x->S == S && x->op == op && x->poly == crc_poly && x->want_crc == want_crc && x->data_only == data_only &&
+        x->state == CoBatch::OPEN && x->claimed < x->cap) {
+      b = x;
+      break;
+    }
+  if (!b) {
+    if (!q.pool.empty()) {
+      b = q.pool.back();
+      q.pool.pop_back();
+    } else {
+      b = new CoBatch();
+    }
+    b->h = h;
+    b->S = S;
+    b->P = P;
+    b->n = n;
+    b->op = op;
+    b->poly = crc_poly;
+    b->want_crc = want_crc;
+    b->data_only = data_only;
+    b->cap = cap;
+    b->claimed = b->filled = b->left = 0;
+    b->state = CoBatch::OPEN;
+    b->rc = CUBEEC_OK;
+    if (op == 1) b->present.assign((size_t)cap * n, 1);
+    b->deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(std::max(0, g_co_delay_us.load()));
+    const size_t need = dstripe * (size_t)cap, need_crc = (size_t)cap * n * 4;
+    if (need > b->h_cap || need_crc > b->crc_cap) {
+      lk.unlock();   // pinned allocation is slow: not under the queue lock
+      if (b->h_buf) cudaFreeHost(b->h_buf);
+      if (b->h_crc) cudaFreeHost(b->h_crc);
+      b->h_buf = nullptr;
+      b->h_crc = nullptr;
+      b->h_cap = b->crc_cap = 0;
+      cudaSetDevice(q.ctx->device);
+      cudaError_t e = cudaMallocHost(&b->h_buf, need);
+      if (e == cudaSuccess) e = cudaMallocHost(&b->h_crc, need_crc);
+      lk.lock();
+      if (e != cudaSuccess) {
         if (b->h_buf) cudaFreeHost(b->h_buf);
-        if (b->h_crc) cudaFreeHost(b->h_crc);
         b->h_buf = nullptr;
-        b->h_crc = nullptr;
-        b->h_cap = b->crc_cap = 0;
-        cudaSetDevice(q.ctx->device);
-        cudaError_t e = cudaMallocHost(&b->h_buf, need);
-        if (e == cudaSuccess) e = cudaMallocHost(&b->h_crc, need_crc);
-        lk.lock();
-        if (e != cudaSuccess) {
-          if (b->h_buf) cudaFreeHost(b->h_buf);
-          b->h_buf = nullptr;
-          q.pool.push_back(b);
-          return cuda_fail(e, "cudaMallocHost(coalescing batch)");
-        }
-        b->h_cap = need;
-        b->crc_cap = need_crc;
+        q.pool.push_back(b);
+        *rc_out = cuda_fail(e, "cudaMallocHost(coalescing batch)");
+        return nullptr;
       }
-      q.open.push_back(b);
-      q.pending.push_back(b);
+      b->h_cap = need;
+      b->crc_cap = need_crc;
     }
-    idx = b->claimed++;
-    b->left++;
-    if (b->claimed == b->cap) {
-      b->state = CoBatch::CLOSED;
-      q.open.erase(std::remove(q.open.begin(), q.open.end(), b), q.open.end());
-    }
-    if (idx == 0) q.work_cv.notify_one();   // a worker has to watch the new deadline
+    q.open.push_back(b);
+    q.pending.push_back(b);
   }
+  const int idx = b->claimed++;
+  b->left++;
+  if (b->claimed == b->cap) {
+    b->state = CoBatch::CLOSED;
+    q.open.erase(std::remove(q.open.begin(), q.open.end(), b), q.open.end());
+  }
+  if (idx == 0) q.work_cv.notify_one();   // a worker has to watch the new deadline
+  *idx_out = idx;
+  return b;
+}
+
+// After the slot has been filled: wait for the batch, return its result.
+int co_wait(CoBatch* b) {
+  CoQueue& q = g_co;
+  std::unique_lock<std::mutex> lk(q.mu);
+  b->filled++;
+  if (b->filled == b->claimed) q.work_cv.notify_all();
+  b->done_cv.wait(lk, [&] { return b->state == CoBatch::DONE; });
+  if (b->rc) t_last_error = b->err;
+  return b->rc;
+}
+void co_release(CoBatch* b) {
+  CoQueue& q = g_co;
+  std::lock_guard<std::mutex> lk(q.mu);
+  if (--b->left == 0) q.pool.push_back(b);   // last caller out recycles the batch (pinned buffers stay allocated)
+}
+int co_cap(size_t S, int n) {
+  const int max_batch = g_co_max_batch.load();
+  if (max_batch <= 1) return 0;
+  return (int)std::min<size_t>((size_t)max_batch, std::max<size_t>(1, kCoBatchBytes / (round_up(S, kAlign) * (size_t)n)));
+}
+
+// cubeec_encode through the queue.  Returns -1 when the call is not eligible (queue off, m == 0, ...).
+int co_encode(cubeec* h, uint8_t* const* shards, size_t S, int n, uint32_t* crc_out, int crc_poly) {
+  const int cap = co_cap(S, n);
+  if (cap <= 1 || h->m == 0) return -1;   // (stripes this large are a batch by themselves)
+  int idx = 0, rc = CUBEEC_OK;
+  CoBatch* b = co_claim(h, S, n, 0, crc_out != nullptr, crc_poly, false, cap, &idx, &rc);
+  if (!b) return rc;
   // fill the slot from the caller's (pageable) memory, in the caller's thread
-  uint8_t* slot = b->h_buf + (size_t)idx * dstripe;
+  const size_t P = b->P;
+  uint8_t* slot = b->h_buf + (size_t)idx * P * n;
   for (int i = 0; i < h->k; i++) std::memcpy(slot + (size_t)i * P, shards[i], S);
-  int rc;
-  {
-    std::unique_lock<std::mutex> lk(q.mu);
-    b->filled++;
-    if (b->filled == b->claimed) q.work_cv.notify_all();
-    b->done_cv.wait(lk, [&] { return b->state == CoBatch::DONE; });
-    rc = b->rc;
-    if (rc) t_last_error = b->err;
-  }
+  rc = co_wait(b);
   if (rc == CUBEEC_OK) {
     for (int i = h->k; i < n; i++) std::memcpy(shards[i], slot + (size_t)i * P, S);
     if (crc_out) std::memcpy(crc_out, b->h_crc + (size_t)idx * n, (size_t)n * 4);
   }
-  {
-    std::lock_guard<std::mutex> lk(q.mu);
-    if (--b->left == 0) q.pool.push_back(b);   // last caller out recycles the batch (pinned buffers stay allocated)
+  co_release(b);
+  return rc;
+}
+
+// cubeec_reconstruct through the queue (degraded reads: stream_get.go:454-465 calls ReconstructData per blob, from
+// many goroutines, and one dead node gives every call the same erasure pattern -> one pattern per batch -> the run-time
+// compiled kernel).  Returns -1 when not eligible (queue off, checksums requested).
+int co_reconstruct(cubeec* h, uint8_t* const* shards, const uint8_t* present, size_t S, int n, bool data_only, uint8_t* filled) {
+  const int cap = co_cap(S, n);
+  if (cap <= 1) return -1;
+  int idx = 0, rc = CUBEEC_OK;
+  CoBatch* b = co_claim(h, S, n, 1, false, 0, data_only, cap, &idx, &rc);
+  if (!b) return rc;
+  const size_t P = b->P;
+  uint8_t* slot = b->h_buf + (size_t)idx * P * n;
+  for (int i = 0; i < n; i++) {
+    b->present[(size_t)idx * n + i] = present[i] ? 1 : 0;   // this slot's flags: nobody else touches them
+    if (present[i]) std::memcpy(slot + (size_t)i * P, shards[i], S);
   }
+  rc = co_wait(b);
+  if (rc == CUBEEC_OK) {
+    for (int i = 0; i < n; i++)
+      if (!present[i] && !(data_only && i >= h->k)) {
+        std::memcpy(shards[i], slot + (size_t)i * P, S);
+        if (filled) filled[i] = 1;
+      }
+  }
+  co_release(b);
   return rc;
 }
 
@@ -2024,6 +2108,16 @@ extern "C" int cubeec_reconstruct(cubeec_t* h, uint8_t* const* shards, const siz
   std::vector<uint8_t> present(n);
   for (int i = 0; i < n; i++) present[i] = lens[i] != 0;
   if ((rc = ensure_init())) return rc;
+  if (!crc_out) {
+    // the cases that need no device work, decided as RS/reedsolomon.go:1434-1444 does, then the coalescing queue
+    int number_present = 0, data_present = 0;
+    for (int i = 0; i < n; i++)
+      if (present[i]) { number_present++; if (i < h->k) data_present++; }
+    if (number_present == n || (data_only && data_present == h->k)) return CUBEEC_OK;
+    if (number_present < h->k) return CUBEEC_ERR_TOO_FEW_SHARDS;
+    rc = co_reconstruct(h, shards, present.data(), S, n, data_only != 0, filled);
+    if (rc >= 0) return rc;
+  }
   DevCtx* c = g.ctx[0].get();
   LaneLease lease;
   if ((rc = lease.acquire(c))) return rc;

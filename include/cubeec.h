@@ -101,11 +101,13 @@ int cubeec_decode_matrix(const cubeec_t* h, const uint8_t* present /* k+m */, in
 int cubeec_encode(cubeec_t* h, uint8_t* const* shards, const size_t* lens, int n,
                   uint32_t* crc_out, int crc_poly);
 
-/* Coalescing of concurrent single-stripe cubeec_encode calls (the shape access uses: one blob per Encode call
+/* Coalescing of concurrent single-stripe cubeec_encode / cubeec_reconstruct calls (the shape access uses: one blob per call
  * from up to 1000 goroutines, BS/common/ec/encoder.go:114-131, BS/access/stream/config_defaulter.go:24).  Callers
  * block in the call; the library gathers up to max_batch stripes of the same code / shard size that arrive within
  * delay_us of the first one into ONE H2D copy, ONE device encode (+ fused CRC) and ONE D2H copy, staged through
- * pinned memory that the callers fill and drain in parallel.  Defaults: 32 stripes, 100 us.  max_batch <= 1
+ * pinned memory that the callers fill and drain in parallel (cubeec_reconstruct without crc_out: survivors in, one
+ * batched device reconstruct -- one pattern per batch runs the kernel compiled for it -- regenerated shards out).
+ * Defaults: 32 stripes, 100 us.  max_batch <= 1
  * disables the queue: every call then performs its own round trip. */
 int cubeec_set_coalescing(int max_batch, int delay_us);
 

@@ -268,3 +268,55 @@ def test_lrc_verify_and_reconstruct_on_device(cb, oracle, mode):
                     assert np.array_equal(out[s, i, :S], host[s, i, :S]), (mode, s, i, data_only)
                 else:
                     assert np.array_equal(out[s, i, :S], broken[s, i, :S]), (mode, s, i, "left missing")
+
+
+@pytest.mark.parametrize("coalesce", [(32, 100), (1, 0)])
+def test_concurrent_degraded_read_callers(cb, oracle, coalesce):
+    """48 threads calling cubeec_reconstruct (ReconstructData and Reconstruct, stream_get.go:454-465) at once: the queue
+    batches calls of the same code / size / flavour; most share one erasure pattern (a dead node), some do not; a few ask
+    for checksums (direct path).  Every regenerated shard must equal the original, `filled` semantics included."""
+    cb.set_coalescing(*coalesce)
+    try:
+        k, m = 12, 4
+        n = k + m
+        eng = cb.RSEngine(k, m)
+        ora = oracle.RS(k, m)
+        errors = []
+
+        def worker(i):
+            try:
+                rng = np.random.default_rng(7000 + i)
+                for it in range(5):
+                    S = [349526, 21846, 2048 + 6][(i + it) % 3]
+                    sh = [rng.integers(0, 256, S, dtype=np.uint8) for _ in range(k)] + [np.zeros(S, np.uint8) for _ in range(m)]
+                    ora.encode(sh)
+                    miss = [3] if (i + it) % 4 else sorted(rng.choice(n, size=int(rng.integers(1, m + 1)), replace=False).tolist())
+                    data_only = (it % 2 == 1)
+                    broken = [None if j in miss else sh[j].copy() for j in range(n)]
+                    if it == 4 and i % 5 == 0:
+                        out, crc = eng.reconstruct(broken, data_only=data_only, crc=True)
+                    else:
+                        out, crc = eng.reconstruct(broken, data_only=data_only), None
+                    for j in range(n):
+                        if j in miss and data_only and j >= k:
+                            assert out[j] is None, (i, it, j, "parity must stay missing with ReconstructData")
+                        else:
+                            assert out[j] is not None and (out[j] == sh[j]).all(), (i, it, j)
+                            if crc is not None and j in miss:
+                                assert int(crc[j]) == zlib.crc32(sh[j].tobytes()), (i, it, j)
+            except Exception as e:   # noqa: BLE001
+                errors.append(repr(e))
+
+        th = [threading.Thread(target=worker, args=(i,)) for i in range(48)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errors, errors[:3]
+        # too few shards is still reported before anything is queued
+        sh = [None] * 5 + [np.zeros(64, np.uint8)] * 11
+        with pytest.raises(cb.CubeecError) as e:
+            eng.reconstruct(sh)
+        assert e.value.name == "ErrTooFewShards"
+    finally:
+        cb.set_coalescing(32, 100)

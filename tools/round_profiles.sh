@@ -12,12 +12,15 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:rs_b
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"rs_bs_kernel" -s 3 -c 1 -o /tmp/bs_nocrc $B --no-extra --crc 0 > $O/ncu_bs.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rs_tabk -s 3 -c 1 -o /tmp/tabk_rec $B --no-extra --workload reconstruct > $O/ncu_tabk.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rs_jit -s 3 -c 1 -o /tmp/jit_rec $B > $O/ncu_jit.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:rs_bssyn -s 3 -c 1 -o /tmp/syn_rec $B --no-extra --workload reconstruct --force 9 > $O/ncu_syn.log 2>&1
 python tools/ncu_summary.py /tmp/bsf_crc.ncu-rep > $O/${R}_prof_bsf_crc.txt 2>&1
 python tools/ncu_summary.py /tmp/bs_nocrc.ncu-rep > $O/${R}_prof_bs_nocrc.txt 2>&1
 python tools/ncu_summary.py /tmp/tabk_rec.ncu-rep > $O/${R}_prof_tabk_rec.txt 2>&1
 python tools/ncu_summary.py /tmp/jit_rec.ncu-rep > $O/${R}_prof_jit_rec.txt 2>&1
+python tools/ncu_summary.py /tmp/syn_rec.ncu-rep > $O/${R}_prof_bssyn_cpasync.txt 2>&1
 timeout 400 python bench.py > $O/${R}_bench_encode_crc.json 2> $O/bench.err; tail -2 $O/bench.err
 timeout 300 python bench.py --workload reconstruct --no-e2e > $O/${R}_bench_reconstruct.json 2>/dev/null
+timeout 300 python bench.py --workload reconstruct --no-e2e --no-cpu --no-extra --force 9 > $O/${R}_bench_reconstruct_bssyn.json 2>/dev/null
 timeout 300 python bench.py --impl reference > $O/${R}_bench_reference_arm.json 2>/dev/null
 timeout 400 python tools/sweep.py > $O/${R}_sweep_c4_c5.jsonl 2>/dev/null
 timeout 400 python tools/sweep.py --modes > $O/${R}_sweep_code_modes.jsonl 2>/dev/null
