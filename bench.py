@@ -224,6 +224,43 @@ def cpu_baseline(workload, stripes_sample, target_seconds=12.0):
             "sample": f"{stripes_sample} stripes x {reps} passes, {el:.1f} s, {leg.describe()}"}
 
 
+def cpu_single_call(blob, seconds=3.0):
+    """The CPU side of e2e_single_call: T = host-core-count threads, each encoding ONE blob per call with the oracle's SIMD
+    port (parity + CRC32 of all shards, one thread per call -- klauspost would split a call over up to 8 goroutines,
+    RS/reedsolomon.go:551-557, which changes latency, not the all-cores throughput reported here)."""
+    from oracle import pyoracle
+    S = shard_size(blob, K)
+    n = K + M
+    rs = pyoracle.RS(K, M)
+    T = len(os.sched_getaffinity(0)) or 1
+    rng = np.random.default_rng(1)
+    bufs = [rng.integers(0, 256, (1, n, S), dtype=np.uint8) for _ in range(T)]
+    crcs = [np.zeros((1, n), dtype=np.uint32) for _ in range(T)]
+    lat = [[] for _ in range(T)]
+    stop = [False]
+
+    def worker(t):
+        while not stop[0]:
+            t0 = time.perf_counter()
+            rs.encode_batch_simd(bufs[t], S, S, n * S, 1, threads=1, crc_out=crcs[t])
+            lat[t].append(time.perf_counter() - t0)
+
+    th = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(T)]
+    t0 = time.perf_counter()
+    for x in th:
+        x.start()
+    time.sleep(seconds)
+    stop[0] = True
+    for x in th:
+        x.join()
+    el = time.perf_counter() - t0
+    allv = np.sort(np.concatenate([np.asarray(v) for v in lat if v]))
+    calls = int(allv.size)
+    return {"threads": T, "calls": calls, "stripes_per_s": round(calls / el, 1), "data_GiB_per_s": round(calls * K * S / el / GIB, 3),
+            "p50_ms": round(float(allv[calls // 2]) * 1e3, 3), "p99_ms": round(float(allv[min(calls - 1, int(calls * 0.99))]) * 1e3, 3),
+            "impl": f"oracle SIMD port ({rs.simd_kind()}), one stripe and one thread per call"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is Go
     (no toolchain here), so this is the oracle's SIMD port on all host cores; rank 0 only."""
@@ -513,6 +550,8 @@ def main():
         if world == 1 and hasattr(eng, "encode_single_call_bench"):
             e2e_single = eng.encode_single_call_bench(BLOB, [int(x) for x in args.single_threads.split(",")],
                                                       check=not args.no_check)
+            if not args.no_cpu:
+                e2e_single["cpu_same_call_shape"] = cpu_single_call(BLOB)
 
     if rank == 0:
         alg = ((K + M) if args.workload == "encode" else (K + erasures)) * S * ns
