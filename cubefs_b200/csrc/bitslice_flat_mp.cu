@@ -14,13 +14,13 @@ bool bsf_mp_supported(int k, int m, int pass, int crc_mode) {
   return false;
 }
 
-cudaError_t launch_bsf_mp(int k, int m, int pass, int crc_mode, const BsfParams& p, int grid, cudaStream_t st) {
+cudaError_t launch_bsf_mp(int k, int m, int pass, int crc_mode, const BsfParams& p, int grid, cudaStream_t st, int flip) {
 #define X(KK, MM, VV, MT, RR, PP, PL)                                              \
   if constexpr (PL == 0) {                                                         \
     if (k == KK && m == MT && pass == PP) {                                        \
-      if (crc_mode == 2) return bsf_launch_one<KK, MM, VV, 2>(p, grid, st);        \
+      if (crc_mode == 2) return bsf_launch_one<KK, MM, VV, 2>(p, grid, st, flip);      \
       if constexpr (RR == 0) {                                                     \
-        if (crc_mode == 1) return bsf_launch_one<KK, MM, VV, 1>(p, grid, st);      \
+        if (crc_mode == 1) return bsf_launch_one<KK, MM, VV, 1>(p, grid, st, flip);    \
       }                                                                            \
       return cudaErrorInvalidValue;                                                \
     }                                                                              \

@@ -85,7 +85,7 @@ __host__ __device__ __forceinline__ uint64_t bsf_owner(uint64_t u, uint64_t U, u
 // traffic costs more than the aliasing.  Not kept.
 // (Warp counts between 12 and 16 do not exist for this kernel: registers are per scheduler, 16 K each, so 4 warps per
 // scheduler cap a thread at 128 registers and 3 at 168; ptxas picks exactly those two.)
-template <int K, int M, int V, int CRC, int NT, int RD, bool PF = false>
+template <int K, int M, int V, int CRC, int NT, int RD, bool PF = false, int ENTRY = 0>
 __device__ __forceinline__ void bsf_body(const BsfParams& p) {
   static_assert(CRC == 1 || CRC == 2, "fused-CRC kernel");
   static_assert(K >= 2 && K + M <= 32, "lane q publishes the remainder of shard q");
@@ -323,6 +323,15 @@ __device__ __forceinline__ void bsf_body(const BsfParams& p) {
       const uint32_t s2 = wrap ? s + 1 : s, t2 = wrap ? 0u : t + 1;
       const bool more = u + 1 < u_hi;
       const bool full = (t + 1) * (32u * kBsPiece) <= p.shard_len;   // warp-uniform
+      // p.sync_units: the warps of the block start every unit together.  The straight-line body of a long code is
+      // several times the SM's 32 KB instruction cache (124 KB for RS(12,4), 182 KB for RS(20,4)); in step, one fetch
+      // from L2 can serve all 12 warps instead of one each.  Measured on B200 (with the grid-constant entry):
+      // RS(20,4) 0.437 -> 0.494, RS(16,4) 0.48 -> 0.51, RS(12,4) C2 0.528 -> 0.543; k <= 10 loses 10-15 %.  Finer
+      // barriers (per column, per shard), warp groups on named barriers, and a rolled shard loop whose body fits the
+      // cache (networks behind a switch) were all slower.  Only the grid-constant entry carries the test.
+      if constexpr (ENTRY == 1) {
+        if (p.sync_units) __syncthreads();
+      }
 #pragma unroll 1
       for (uint32_t g = 0; g < 2; g++) {
         const Col cc = locate(s, t, g);
@@ -345,14 +354,40 @@ __device__ __forceinline__ void bsf_body(const BsfParams& p) {
     }
     flush(t == 0 ? s - 1 : s);   // (s, t) is one unit past the run: the last unit's stripe
   }
+  if constexpr (ENTRY == 1) {
+    if (p.sync_units) {
+      // runs are floor(U / GW) or one more units long: the shorter ones still owe the block their barriers
+      const uint64_t longest = (U + GW - 1) / GW;
+      for (uint64_t i = u_hi - u_lo; i < longest; i++) __syncthreads();
+    }
+  }
 }
+// Two entry points over the same body: parameters by value (ENTRY 0), or __grid_constant__ with the per-unit barrier
+// (ENTRY 1).  How the parameter block is addressed changes nothing semantically, but the schedule ptxas finds for this
+// register-bound kernel follows it.  Measured on B200 (fraction of the measured HBM peak, fused encode + CRC,
+// profiles/r02_sweep_bsf_entry_sync.jsonl): RS(12,4) C2 0.531 by value / 0.528 grid-constant / 0.543 + barrier;
+// RS(16,4) 0.43 / 0.48 / 0.51; RS(20,4) 0.396 / 0.437 / 0.494; RS(24,8) passes 0.26 / - / 0.28; k <= 10: by value.
 template <int K, int M, int V, int CRC, int NT, int RD = (NT <= 384 ? 4 : 3)>
 __global__ void __launch_bounds__(NT, 1) rs_bsf_kernel(const BsfParams p) {
-  bsf_body<K, M, V, CRC, NT, RD>(p);
+  bsf_body<K, M, V, CRC, NT, RD, false, 0>(p);
 }
+template <int K, int M, int V, int CRC, int NT, int RD = (NT <= 384 ? 4 : 3)>
+__global__ void __launch_bounds__(NT, 1) rs_bsf_kernel_gc(const __grid_constant__ BsfParams p) {
+  bsf_body<K, M, V, CRC, NT, RD, false, 1>(p);   // (its own instantiation of the body, so that both entries inline theirs)
+}
+constexpr bool bsf_has_gc_entry(int k, int m, int v, int mode) { return (m == 4 && v == 0 && mode == 1) || k >= 15; }
+// flip (cubeec_debug_force_kernel(3000 + bits), A/B aid): bit 0 the entry, bit 1 the barrier
 template <int K, int M, int V, int MODE, int NT = kBsfThreads>
-static cudaError_t bsf_launch_one(const BsfParams& p, int grid, cudaStream_t st) {
-  auto kern = rs_bsf_kernel<K, M, V, MODE, NT>;
+static cudaError_t bsf_launch_one(const BsfParams& p0, int grid, cudaStream_t st, int flip = 0) {
+  BsfParams p = p0;
+  p.sync_units = 0;
+  void (*kern)(const BsfParams) = rs_bsf_kernel<K, M, V, MODE, NT>;
+  if constexpr (bsf_has_gc_entry(K, M, V, MODE)) {
+    if ((K >= 12) != ((flip & 1) != 0)) {
+      kern = rs_bsf_kernel_gc<K, M, V, MODE, NT>;
+      p.sync_units = ((K >= 12) != ((flip & 2) != 0)) ? 1u : 0u;
+    }
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsfSmemBytes);
   if (e != cudaSuccess) return e;
   kern<<<grid, NT, kBsfSmemBytes, st>>>(p);

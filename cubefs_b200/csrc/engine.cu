@@ -723,7 +723,7 @@ struct FlatGeometry {
   uint32_t units_per_shard = 0;
   uint64_t total_units = 0, total_warps = 0;
   uint32_t max_parts = 0;
-  int grid = 0, threads = kBsfThreads;
+  int grid = 0, threads = kBsfThreads, variant = kBsfThreads;
 };
 
 int bsf_threads() {
@@ -731,9 +731,16 @@ int bsf_threads() {
   return (f >= 1000 && f < 2000) ? f - 1000 : kBsfThreads;   // cubeec_debug_force_kernel(1000 + variant): A/B aid
 }
 
+// cubeec_debug_force_kernel(3000 + bits): bit 0 flips the parameter-passing entry, bit 1 the per-unit barrier (A/B aid)
+int bsf_flip() {
+  const int f = g_force_kernel.load();
+  return (f >= 3000 && f < 3004) ? f - 3000 : 0;
+}
+
 FlatGeometry flat_geometry(const DevCtx& c, size_t shard_len, size_t n_stripes) {
   FlatGeometry fg;
-  fg.threads = bsf_threads();
+  fg.variant = bsf_threads();
+  fg.threads = fg.variant & ~31;
   const uint64_t nw = (uint64_t)fg.threads / 32;
   fg.units_per_shard = (uint32_t)((shard_len + kBsfUnitBytes - 1) / kBsfUnitBytes);
   fg.total_units = (uint64_t)n_stripes * fg.units_per_shard;
@@ -789,8 +796,8 @@ int bsf_run(cubeec* h, DevCtx& c, cudaStream_t stream, uint8_t* d_base, size_t s
     }
     for (int r = 0; r < rows && r < (int)sizeof(bp.out_slot); r++) bp.out_slot[r] = (uint8_t)(out_first + r0 + r);
     const int mode = (crc == 1 && pass == 0) ? 1 : 2;
-    if (fg.threads != kBsfThreads && h->k == 12 && h->m == 4 && mode == 1) CU(launch_bsf_variant(fg.threads, bp, fg.grid, stream));
-    else CU(launch_bsf(h->k, h->m, pass, mode, bp, fg.grid, stream));
+    if (fg.variant != kBsfThreads && h->k == 12 && h->m == 4 && mode == 1) CU(launch_bsf_variant(h->k, fg.variant, bp, fg.grid, stream));
+    else CU(launch_bsf(h->k, h->m, pass, mode, bp, fg.grid, stream, bsf_flip()));
     g_launches++;
   }
   t_last_kernel = "rs_bsf_kernel<crc>";

@@ -186,6 +186,7 @@ struct BsfParams {
   uint64_t total_units;               // n_stripes * units_per_shard
   uint32_t max_parts;
   uint32_t poly;
+  uint32_t sync_units;                // set by the launcher (bs_flat.cuh): block-wide barrier at the top of every unit
   uint32_t* crc_part;
   uint8_t in_slot[24];
   uint8_t out_slot[8];
@@ -209,9 +210,9 @@ struct CrcPartsFinalizeParams {
 cudaError_t launch_crc_parts_finalize(const CrcPartsFinalizeParams& p, cudaStream_t stream);
 // does bitslice_flat.cu have RS(k, m) pass `pass` of plan 0 with this CRC mode (1 all shards, 2 outputs only)?
 bool bsf_supported(int k, int m, int pass, int crc_mode);
-cudaError_t launch_bsf(int k, int m, int pass, int crc_mode, const BsfParams& p, int grid, cudaStream_t st);
+cudaError_t launch_bsf(int k, int m, int pass, int crc_mode, const BsfParams& p, int grid, cudaStream_t st, int flip = 0);
 // A/B measurement aid: RS(12,4) mode 1 with another CTA size (threads in {512, 448, 384, 320, 256})
-cudaError_t launch_bsf_variant(int threads, const BsfParams& p, int grid, cudaStream_t st);
+cudaError_t launch_bsf_variant(int k, int variant, const BsfParams& p, int grid, cudaStream_t st);
 
 
 // ---- generic bit-sliced coding kernel (bitslice_gen.cu): run-time coefficients, flat work split -------

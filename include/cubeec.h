@@ -257,6 +257,8 @@ const char* cubeec_last_kernel(void);
  * 6 = rolled-loop fused encode+CRC kernel (smaller hot loop; RS(12,4), (10,4), (6,2)),
  * 7 = tile-split fused kernel rs_bs_kernel<crc> for every shard size (default: the flat-split rs_bsf_kernel from
  * 16 KiB), 1000+T = flat-split fused kernel with T threads per CTA (RS(12,4) only),
+ * 3000+b = flat-split fused kernel with its measured picks flipped: bit 0 the entry point (parameters by value /
+ * __grid_constant__), bit 1 the per-unit block barrier (bs_flat.cuh),
  * 4 = no run-time compiled (NVRTC) reconstruct kernels: single-pattern batches take the table kernels too,
  * 9 = flat-split bit-sliced syndrome kernel (rs_bssyn_kernel) for cubeec_dev_reconstruct. */
 void cubeec_debug_force_kernel(int which);

@@ -77,6 +77,7 @@ def main():
     ap.add_argument("--gpu", type=int, default=0)
     ap.add_argument("--crc", type=int, default=1)
     ap.add_argument("--gib", type=float, default=2.0, help="batch size per case (GiB in HBM)")
+    ap.add_argument("--forces", default="", help="comma list of cubeec_debug_force_kernel values to run every case under")
     ap.add_argument("--modes", action="store_true",
                     help="instead of the C4/C5 shard-size sweep: every predefined EC code mode (codemode.go:65-94) at "
                          "1 MiB shards, bit-sliced path and (A/B) the table kernels")
@@ -99,7 +100,9 @@ def main():
         cases = [(k, m, 1 << 20) for (k, m) in ((15, 12), (6, 6), (16, 20), (6, 10), (6, 3), (4, 4), (12, 4), (16, 4), (3, 3),
                                                  (10, 4), (12, 9), (24, 8), (6, 8))]
         forces = [0, 1]
-    if args.modes:
+    if args.forces:
+        forces = [int(x) for x in args.forces.split(",")]
+    if args.modes and not args.forces:
         # LRC modes: global + per-AZ local passes fused on the device (cubeec_dev_lrc_encode)
         for (N, M, L, az) in ((16, 20, 2, 2), (6, 10, 2, 2), (6, 3, 3, 3), (4, 4, 2, 2)):
             S = 1 << 20
@@ -136,7 +139,7 @@ def main():
             cb.force_kernel(0)
             moved = (k + m) * S * ns / (ms * 1e-3) / 1e9
             if RANK == 0:
-                print(json.dumps({"k": k, "m": m, "shard_bytes": S, "stripes_per_gpu": ns, "n_gpus": WORLD, "crc": bool(crc), "kernel": kern,
+                print(json.dumps({"k": k, "m": m, "shard_bytes": S, "stripes_per_gpu": ns, "n_gpus": WORLD, "crc": bool(crc), "kernel": kern, "force": force,
                                   "ms": round(ms, 4), "data_GiB_s_all_gpus": round(WORLD * k * S * ns / (ms * 1e-3) / 2**30, 1),
                                   "moved_GB_s_per_gpu": round(moved, 1), "frac_of_measured_hbm": round(moved / pk, 4),
                                   "frac_nominal_8TBs": round(moved / 8000.0, 4)}), flush=True)
