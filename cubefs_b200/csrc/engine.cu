@@ -2207,6 +2207,62 @@ extern "C" int cubeec_reconstruct_batch_crc(cubeec_t* h, const cubeec_stripe_t* 
 // and partitioned over the configured devices.
 // ------------------------------------------------------------------------------------------
 namespace {
+bool crc_flat_usable(size_t len) { return g_force_kernel.load() != 10 && len < 0xFFFFE000ull; }
+
+// CRC32 of `units` ranges per buffer ([offset + u * stride, + block) clipped to len): crc_flat_kernel unless forced off
+// (cubeec_debug_force_kernel(10): the first-generation crc_range_kernel) or the buffer is within 8 KiB of 4 GiB.
+int run_crc_ranges(DevCtx& c, cudaStream_t st, const uint8_t* d_base, size_t pitch, size_t n_buffers, size_t len, size_t block,
+                   size_t stride, size_t offset, size_t units, int crc_poly, uint32_t* d_out) {
+  const int pi = crc_poly ? 1 : 0;
+  const uint64_t total = (uint64_t)n_buffers * units;
+  if (crc_flat_usable(len) && total < 0xFFFFFFFFull) {
+    const CrcPoly& P = g.poly[pi];
+    CrcFlatParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.base = d_base;
+    p.pitch = pitch;
+    p.n_buffers = (uint32_t)n_buffers;
+    p.len = (uint32_t)len;
+    p.block = (uint32_t)block;
+    p.units_per_buffer = (uint32_t)units;
+    p.stride = (uint32_t)stride;
+    p.offset = (uint32_t)offset;
+    const size_t step = stride ? stride : block;
+    const bool aligned = offset % kBsfUnitBytes == 0 && (units == 1 || step % kBsfUnitBytes == 0);
+    p.tiles_per_range = (uint32_t)((std::min(block, len) + kBsfUnitBytes - 1) / kBsfUnitBytes + (aligned ? 0 : 1));
+    p.total_tiles = total * p.tiles_per_range;
+    p.poly = P.poly;
+    p.init_full = P.mul(0xFFFFFFFFu, P.shift_bytes_const((int64_t)block));
+    p.out = d_out;
+    p.slice_image = c.d_bs_slice[pi];
+    p.fold_tables = c.d_bsf_fold[pi];
+    p.klane = c.d_bsf_klane[pi];
+    for (int i = 0; i < 24; i++) p.x_unit_pow[i] = P.shift_bytes_const((int64_t)kBsfUnitBytes << i);
+    for (int i = 0; i < 33; i++) p.x_neg_pow[i] = P.shift_bytes_const(-((int64_t)1 << i));
+    CU(cudaMemsetAsync(d_out, 0, total * 4, st));
+    CU(launch_crc_flat(p, c.sm_count, st));
+    g_launches += 2;
+    t_last_kernel = "crc_flat_kernel";
+    return CUBEEC_OK;
+  }
+  CrcRangeParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.base = d_base;
+  p.pitch = pitch;
+  p.n_buffers = (uint32_t)n_buffers;
+  p.len = (uint32_t)len;
+  p.block = (uint32_t)block;
+  p.units_per_buffer = (uint32_t)units;
+  p.crc = c.d_crc[pi];
+  p.out = d_out;
+  p.stride = (uint32_t)stride;
+  p.offset = (uint32_t)offset;
+  CU(launch_crc_ranges(p, (int)std::min<uint64_t>(total, (uint64_t)c.sm_count * 4), st));
+  g_launches++;
+  t_last_kernel = "crc_range_kernel";
+  return CUBEEC_OK;
+}
+
 int dev_crc32_impl(DevCtx& c, cudaStream_t st, const uint8_t* d_base, size_t len, size_t pitch, size_t n_buffers,
                    size_t block, int crc_poly, uint32_t* d_whole, uint32_t* d_blocks);
 
@@ -2354,30 +2410,19 @@ extern "C" int cubeec_lrc_encode_contig(cubeec_t* global, cubeec_t* local, int a
 namespace {
 int dev_crc32_impl(DevCtx& c, cudaStream_t st, const uint8_t* d_base, size_t len, size_t pitch, size_t n_buffers,
                    size_t block, int crc_poly, uint32_t* d_whole, uint32_t* d_blocks) {
-  // internal unit: the caller's block, or 64 KiB slices when only the whole CRC is wanted
-  const size_t unit = block ? block : std::min<size_t>(len, 1u << 16);
+  // internal unit: the caller's block; when only the whole CRC is wanted, the buffer itself (crc_flat_kernel splits it
+  // into tiles on its own) or 64 KiB slices (crc_range_kernel: one CTA per unit)
+  const size_t unit = block ? block : (crc_flat_usable(len) ? len : std::min<size_t>(len, 1u << 16));
   const size_t units = (len + unit - 1) / unit;
+  if (!block && units == 1 && d_whole) return run_crc_ranges(c, st, d_base, pitch, n_buffers, len, unit, 0, 0, 1, crc_poly, d_whole);
   uint32_t* d_units = d_blocks;
   AsyncScratch scratch(st);
   if (!d_units || !block) {
     CU(scratch.alloc(n_buffers * units * 4));
     d_units = static_cast<uint32_t*>(scratch.ptr);
   }
-  CrcRangeParams p;
-  std::memset(&p, 0, sizeof(p));
-  p.base = d_base;
-  p.pitch = pitch;
-  p.n_buffers = (uint32_t)n_buffers;
-  p.len = (uint32_t)len;
-  p.block = (uint32_t)unit;
-  p.units_per_buffer = (uint32_t)units;
-  p.crc = c.d_crc[crc_poly ? 1 : 0];
-  p.out = d_units;
-  const uint64_t total = (uint64_t)n_buffers * units;
-  const int grid = (int)std::min<uint64_t>(total, (uint64_t)c.sm_count * 4);
-  CU(launch_crc_ranges(p, grid, st));
-  g_launches++;
-  t_last_kernel = "crc_range_kernel";
+  int rc = run_crc_ranges(c, st, d_base, pitch, n_buffers, len, unit, 0, 0, units, crc_poly, d_units);
+  if (rc) return rc;
   if (d_whole) {
     CU(launch_crc_combine(d_units, (uint32_t)n_buffers, (uint32_t)units, (uint32_t)len, (uint32_t)unit,
                           g.poly[crc_poly ? 1 : 0].poly, d_whole, st));
@@ -2449,23 +2494,7 @@ bool crc32block_valid_len(size_t block_len) { return block_len > 0 && block_len 
 
 int dev_crc_units(DevCtx& c, cudaStream_t st, const uint8_t* d_base, size_t pitch, size_t n_buffers, size_t len, size_t block,
                   size_t stride, size_t offset, size_t units, int crc_poly, uint32_t* d_out) {
-  CrcRangeParams p;
-  std::memset(&p, 0, sizeof(p));
-  p.base = d_base;
-  p.pitch = pitch;
-  p.n_buffers = (uint32_t)n_buffers;
-  p.len = (uint32_t)len;
-  p.block = (uint32_t)block;
-  p.units_per_buffer = (uint32_t)units;
-  p.crc = c.d_crc[crc_poly ? 1 : 0];
-  p.out = d_out;
-  p.stride = (uint32_t)stride;
-  p.offset = (uint32_t)offset;
-  const uint64_t total = (uint64_t)n_buffers * units;
-  CU(launch_crc_ranges(p, (int)std::min<uint64_t>(total, (uint64_t)c.sm_count * 4), st));
-  g_launches++;
-  t_last_kernel = "crc_range_kernel";
-  return CUBEEC_OK;
+  return run_crc_ranges(c, st, d_base, pitch, n_buffers, len, block, stride, offset, units, crc_poly, d_out);
 }
 
 int dev_crc32block_encode_impl(DevCtx& c, cudaStream_t st, const uint8_t* d_src, size_t len, size_t src_pitch, size_t n_buffers,

@@ -101,6 +101,24 @@ struct CrcRangeParams {
   uint32_t stride;           // distance between unit starts (0 = block: units back to back)
   uint32_t offset;           // start of unit 0 in the buffer
 };
+// crc_flat.cu: the same ranges, lane-private slicing tables and a flat tile split (see there)
+constexpr int kCrcFlatThreads = 1024;
+struct CrcFlatParams {
+  const uint8_t* base;
+  size_t pitch;
+  uint32_t n_buffers, len, block, units_per_buffer, stride, offset;   // as CrcRangeParams
+  uint32_t tiles_per_range;           // 2 KiB windows of the buffer a range can touch (uniform upper bound)
+  uint64_t total_tiles;               // n_buffers * units_per_buffer * tiles_per_range
+  uint32_t poly;
+  uint32_t init_full;                 // 0xFFFFFFFF * x^(8 * block)
+  uint32_t* out;                      // [n_buffers][units_per_buffer]; zero on entry
+  const uint32_t* slice_image;        // BsfParams' tables
+  const uint32_t* fold_tables;
+  const uint32_t* klane;
+  uint32_t x_unit_pow[24];            // x^(8 * 2048 * 2^i)
+  uint32_t x_neg_pow[33];             // x^(-8 * 2^i)
+};
+cudaError_t launch_crc_flat(const CrcFlatParams& p, int sm_count, cudaStream_t stream);
 // crc32block framing kernels (kernels.cu)
 struct Crc32BlockParams {
   const uint8_t* plain;      // plain image: buffer b at plain + b*plain_pitch, plain_len bytes
@@ -177,6 +195,7 @@ constexpr int kBsfFoldCopies = 8;
 constexpr int kBsfThreads = CUBEEC_BSF_THREADS;   // 12 warps x 168 registers: room for the interleaved schedule (bs_flat.cuh)
 constexpr int kBsfUnitBytes = 32 * kBsPiece;   // bytes of a shard per unit
 constexpr size_t kBsfSmemBytes = 65536 + kBsSliceImageBytes + 1024;
+constexpr size_t kCrcFlatSmemBytes = kBsfSmemBytes;
 struct BsfParams {
   uint8_t* base;
   size_t stripe_pitch, shard_pitch;

@@ -260,7 +260,8 @@ const char* cubeec_last_kernel(void);
  * 3000+b = flat-split fused kernel with its measured picks flipped: bit 0 the entry point (parameters by value /
  * __grid_constant__), bit 1 the per-unit block barrier (bs_flat.cuh),
  * 4 = no run-time compiled (NVRTC) reconstruct kernels: single-pattern batches take the table kernels too,
- * 9 = flat-split bit-sliced syndrome kernel (rs_bssyn_kernel) for cubeec_dev_reconstruct. */
+ * 9 = flat-split bit-sliced syndrome kernel (rs_bssyn_kernel) for cubeec_dev_reconstruct,
+ * 10 = first-generation stand-alone CRC kernel (crc_range_kernel) instead of crc_flat_kernel. */
 void cubeec_debug_force_kernel(int which);
 /* Tests: generate and NVRTC-compile (no device needed) the run-time specialised reconstruct kernel of RS(k, m) for
  * a presence pattern.  0 = compiled, 101 = NVRTC not installed, 102 = compile error (log), else CUBEEC_ERR_*. */
