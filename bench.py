@@ -498,6 +498,15 @@ def main():
         extra["verify"] = record(ms_, n * S * ns, cb.last_kernel())
         if not args.no_check and int(dok.sum().item()) != ns:
             raise SystemExit("bench check FAILED: dev_verify rejects a stripe the engine just encoded")
+        # the shard checksums on their own (what a blobnode does on read / inspect, and the replica modes on write)
+        from cubefs_b200.engine import dev_crc32
+        dcrc2 = torch.zeros_like(dcrc)
+        ms_ = timed(lambda: dev_crc32(batch.data_ptr(), S, P, ns * n, d_whole=dcrc2.data_ptr(), stream=stream, device=local_rank), st, wu)
+        extra["crc32_shards"] = record(ms_, n * S * ns, cb.last_kernel())
+        if not args.no_check:
+            if not torch.equal(dcrc2, dcrc):
+                raise SystemExit("bench check FAILED: stand-alone shard CRCs differ from the fused kernel's")
+            extra["crc32_shards"]["checked_shards"] = int(ns * n)
         for name, pres, e in (("reconstruct_3e", present3, 3), ("reconstruct_1pattern", present1, 1)):
             erase(pres)
             ms_ = timed(lambda pres=pres: rec(pres), st, wu)

@@ -61,7 +61,6 @@ for op, n in mix.most_common(12):
 # ---- where the warps wait: SASS instructions with the most stall samples of the top reasons ----
 try:
     cols = {h: i for i, h in enumerate(h2)}
-    print("source page columns:", [h for h in h2][:60])
     samp = cols.get("# Samples") or cols.get("Warp Stall Sampling (All Samples)") or cols.get("Samples")
     stall_cols = [(h, i) for h, i in cols.items() if h.startswith("stall_") or "stall" in h.lower()]
     addr = cols.get("Address")
