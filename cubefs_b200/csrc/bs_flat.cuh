@@ -95,12 +95,20 @@ __device__ __forceinline__ void bsf_body(const BsfParams& p) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // copies of the fold tables (Horner step between units), see bsf_fold_copies()
+  constexpr int FC = K >= 16 ? CUBEEC_FC_HI : CUBEEC_FC_LO;   // (= bsf_fold_copies(K), kernels.cuh)
+  constexpr size_t FTB = 256 * FC * 4;
 
-  // ---- shared memory: [mbarrier | fold tables (kBsfFoldCopies copies)] ... [64K-aligned slice image]
+  // ---- shared memory: [mbarrier | fold tables (FC copies) | slice image].  Nothing here needs more than 128-byte
+  // alignment (a lookup address is base + 256 * byte + 4 * lane, all additions), so the image follows the fold tables
+  // directly: 192 KB with 16 fold copies (160 KB with 8) instead of the 209 KB (193 KB) a 64K-aligned image costs.
+  // The size matters beyond occupancy: 209 KB selects the 228 KB shared-memory carve-out, and what is left of the SM's
+  // 256 KB is the L1 that holds the loads in flight -- measured with that layout: crc_flat_kernel 0.69 -> 0.53 of the
+  // HBM peak, RS(20,4) 0.495 -> 0.476.  (Below the 196 KB carve-out nothing more is gained: 160 KB = 192 KB.)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  uint32_t* fold_s = reinterpret_cast<uint32_t*>(smem + 64);   // [4][256][kBsfFoldCopies]
+  uint32_t* fold_s = reinterpret_cast<uint32_t*>(smem + 128);   // [4][256][FC]
   const uint32_t base_addr = smem_addr(smem);
-  const uint32_t tab_addr = (base_addr + (uint32_t)(64 + 4 * 256 * kBsfFoldCopies * 4) + 65535u) & ~65535u;
+  const uint32_t tab_addr = base_addr + (uint32_t)(128 + 4 * FTB);
   {
     uint8_t* tab_ptr = smem + (tab_addr - base_addr);
     if (tid == 0) {
@@ -123,7 +131,7 @@ __device__ __forceinline__ void bsf_body(const BsfParams& p) {
     for (int i = tid; i < 4 * 256; i += NT) {
       const uint32_t v = p.fold_tables[i];
 #pragma unroll
-      for (int q = 0; q < kBsfFoldCopies; q++) fold_s[i * kBsfFoldCopies + q] = v;
+      for (int q = 0; q < FC; q++) fold_s[i * FC + q] = v;
     }
     uint32_t done = 0;
     while (!done) {
@@ -137,8 +145,8 @@ __device__ __forceinline__ void bsf_body(const BsfParams& p) {
     }
     __syncthreads();
   }
-  const uint32_t lane_base = tab_addr | (uint32_t)(lane * 4);
-  const uint32_t fold_lane = smem_addr(fold_s) + (uint32_t)((lane & (kBsfFoldCopies - 1)) * 4);
+  const uint32_t lane_base = tab_addr + (uint32_t)(lane * 4);
+  const uint32_t fold_lane = smem_addr(fold_s) + (uint32_t)((lane & (FC - 1)) * 4);
   const uint32_t klane = p.klane[lane];   // x^(8 * 64 * (31 - lane)): aligns a lane's remainder to the end of the unit
 
   auto slice4 = [&](uint32_t y) -> uint32_t {
@@ -153,7 +161,7 @@ __device__ __forceinline__ void bsf_body(const BsfParams& p) {
     return t3 ^ t2 ^ t1 ^ t0;
   };
   auto fold = [&](uint32_t u) -> uint32_t {
-    constexpr uint32_t ST = kBsfFoldCopies * 4;
+    constexpr uint32_t ST = FC * 4;
     return lds32(byte_madd<0>(u, ST, ST << 16, fold_lane + 0 * 256 * ST)) ^ lds32(byte_madd<1>(u, ST, ST << 16, fold_lane + 1 * 256 * ST)) ^
            lds32(byte_madd<2>(u, ST, ST << 16, fold_lane + 2 * 256 * ST)) ^ lds32(byte_madd<3>(u, ST, ST << 16, fold_lane + 3 * 256 * ST));
   };
@@ -388,9 +396,10 @@ static cudaError_t bsf_launch_one(const BsfParams& p0, int grid, cudaStream_t st
       p.sync_units = ((K >= 12) != ((flip & 2) != 0)) ? 1u : 0u;
     }
   }
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsfSmemBytes);
+  constexpr size_t smem_bytes = bsf_smem_bytes(bsf_fold_copies(K));
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return e;
-  kern<<<grid, NT, kBsfSmemBytes, st>>>(p);
+  kern<<<grid, NT, smem_bytes, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -65,11 +65,13 @@ __global__ void __launch_bounds__(kCfThreads, 1) crc_flat_kernel(const __grid_co
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // ---- shared memory: [mbarrier | fold tables (kBsfFoldCopies copies)] ... [64K-aligned slice image]   (as bs_flat.cuh)
+  // ---- shared memory: [mbarrier | fold tables (FC copies) | slice image]   (as bs_flat.cuh)
+  constexpr int FC = kCrcFlatFoldCopies;
+  constexpr size_t FTB = 256 * FC * 4;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  uint32_t* fold_s = reinterpret_cast<uint32_t*>(smem + 64);
+  uint32_t* fold_s = reinterpret_cast<uint32_t*>(smem + 128);
   const uint32_t base_addr = smem_addr(smem);
-  const uint32_t tab_addr = (base_addr + (uint32_t)(64 + 4 * 256 * kBsfFoldCopies * 4) + 65535u) & ~65535u;
+  const uint32_t tab_addr = base_addr + (uint32_t)(128 + 4 * FTB);
   {
     uint8_t* tab_ptr = smem + (tab_addr - base_addr);
     if (tid == 0) {
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(kCfThreads, 1) crc_flat_kernel(const __grid_co
     for (int i = tid; i < 4 * 256; i += NT) {
       const uint32_t v = p.fold_tables[i];
 #pragma unroll
-      for (int q = 0; q < kBsfFoldCopies; q++) fold_s[i * kBsfFoldCopies + q] = v;
+      for (int q = 0; q < FC; q++) fold_s[i * FC + q] = v;
     }
     uint32_t done = 0;
     while (!done) {
@@ -102,8 +104,8 @@ __global__ void __launch_bounds__(kCfThreads, 1) crc_flat_kernel(const __grid_co
     }
     __syncthreads();
   }
-  const uint32_t lane_base = tab_addr | (uint32_t)(lane * 4);
-  const uint32_t fold_lane = smem_addr(fold_s) + (uint32_t)((lane & (kBsfFoldCopies - 1)) * 4);
+  const uint32_t lane_base = tab_addr + (uint32_t)(lane * 4);
+  const uint32_t fold_lane = smem_addr(fold_s) + (uint32_t)((lane & (FC - 1)) * 4);
   const uint32_t klane = p.klane[lane];
 
   auto slice4 = [&](uint32_t y) -> uint32_t {
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kCfThreads, 1) crc_flat_kernel(const __grid_co
     return lds32_off<65536 + 128>(a0) ^ lds32_off<65536>(a1) ^ lds32_off<128>(a2) ^ lds32_off<0>(a3);
   };
   auto fold = [&](uint32_t u) -> uint32_t {
-    constexpr uint32_t ST = kBsfFoldCopies * 4;
+    constexpr uint32_t ST = FC * 4;
     return lds32(byte_madd<0>(u, ST, ST << 16, fold_lane + 0 * 256 * ST)) ^ lds32(byte_madd<1>(u, ST, ST << 16, fold_lane + 1 * 256 * ST)) ^
            lds32(byte_madd<2>(u, ST, ST << 16, fold_lane + 2 * 256 * ST)) ^ lds32(byte_madd<3>(u, ST, ST << 16, fold_lane + 3 * 256 * ST));
   };
@@ -227,7 +229,6 @@ __global__ void crc_flat_finish_kernel(const __grid_constant__ CrcFlatParams p) 
 
 // p.out must be zero when crc_flat_kernel starts (the engine clears it on the same stream).
 cudaError_t launch_crc_flat(const CrcFlatParams& p, int sm_count, cudaStream_t stream) {
-  static_assert(kCrcFlatSmemBytes == kBsfSmemBytes, "same shared-memory image as the fused kernel");
   // 256-bit loads need 32-byte aligned buffers, and a pitch that covers the 32-byte chunk holding the last byte
   const bool v8 = ((uintptr_t)p.base % 32 == 0) && (p.pitch % 32 == 0) && (((size_t)p.len + 31) / 32 * 32 <= p.pitch);
   auto kern = v8 ? crc_flat_kernel<true> : crc_flat_kernel<false>;

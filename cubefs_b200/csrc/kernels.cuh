@@ -188,14 +188,29 @@ struct BsParams {
 // Units (2 KiB of every shard of one stripe) are numbered stripe-major; warp g of the grid takes units
 // [g*U/GW, (g+1)*U/GW).  crc_part[((stripe * n_slots + slot) * max_parts + j)] = remainder of the j-th run that
 // touches the stripe (aligned to the end of its last unit there); crc_parts_finalize_kernel chains them.
-constexpr int kBsfFoldCopies = 8;
+// Copies of the 4 x 256-entry fold tables in shared memory (bank conflicts of the Horner step vs shared-memory size).
+// Build-time knobs for A/B builds (tools/ab_fold_copies.sh); the defaults are the measured picks.  B200, fraction of the
+// measured HBM peak, 16 copies / 8 copies: RS(12,4) C2 0.550 / 0.542, 383 stripes 0.518 / 0.512, RS(6,3) 0.635 / 0.627,
+// RS(10,4) 0.555 / 0.552, RS(16,4) 0.515 / 0.511, RS(20,4) 0.498 / 0.493, crc_flat_kernel 0.699 / 0.691.
+#ifndef CUBEEC_FC_LO
+#define CUBEEC_FC_LO 16   /* fused kernel, k < 16 */
+#endif
+#ifndef CUBEEC_FC_HI
+#define CUBEEC_FC_HI 16   /* fused kernel, k >= 16 */
+#endif
+#ifndef CUBEEC_FC_CRC
+#define CUBEEC_FC_CRC 16  /* crc_flat_kernel */
+#endif
+constexpr int bsf_fold_copies(int k) { return k >= 16 ? CUBEEC_FC_HI : CUBEEC_FC_LO; }
+constexpr int kCrcFlatFoldCopies = CUBEEC_FC_CRC;
 #ifndef CUBEEC_BSF_THREADS
 #define CUBEEC_BSF_THREADS 384
 #endif
 constexpr int kBsfThreads = CUBEEC_BSF_THREADS;   // 12 warps x 168 registers: room for the interleaved schedule (bs_flat.cuh)
 constexpr int kBsfUnitBytes = 32 * kBsPiece;   // bytes of a shard per unit
-constexpr size_t kBsfSmemBytes = 65536 + kBsSliceImageBytes + 1024;
-constexpr size_t kCrcFlatSmemBytes = kBsfSmemBytes;
+constexpr size_t bsf_smem_bytes(int fold_copies) { return 128 + (size_t)4 * 256 * fold_copies * 4 + kBsSliceImageBytes; }
+constexpr size_t kBsfSmemBytes = bsf_smem_bytes(16);   // upper bound
+constexpr size_t kCrcFlatSmemBytes = bsf_smem_bytes(kCrcFlatFoldCopies);
 struct BsfParams {
   uint8_t* base;
   size_t stripe_pitch, shard_pitch;
