@@ -117,3 +117,79 @@ def test_const_multiply_tables(hm, poly, order, pid):
         for u in [int(x) for x in rng.integers(0, 1 << 32, 50, dtype=np.uint64)]:
             got = int(t[0][u & 255]) ^ int(t[1][(u >> 8) & 255]) ^ int(t[2][(u >> 16) & 255]) ^ int(t[3][u >> 24])
             assert got == hm.hm_crc_mul(poly, order, u, const)
+
+
+@pytest.mark.parametrize("poly,order,pid", POLYS)
+def test_crc_flat_kernel_decomposition(hm, oracle, poly, order, pid):
+    """The algebra of crc_flat_kernel / crc_flat_finish_kernel (cubefs_b200/csrc/crc_flat.cu) replayed with the constants
+    the engine builds on the host (engine.cu: fold tables x^(8*(2048-64)), klane x^(8*64*(31-lane)), x_unit_pow, x_neg_pow,
+    init term): 2 KiB tiles of the BUFFER, 32 lanes x 64 contiguous bytes, bytes outside [a, e) masked to zero, Horner
+    across the tiles of a run, runs combined by XOR behind x^(8*2048*tiles after), x^(-8z) for the zero bytes behind the
+    range.  Ranges as the crc32block payloads have them: starting 4 bytes into a block, aligned to nothing."""
+    TILE, PIECE = 2048, 64
+    sl = np.zeros((4, 256), dtype=np.uint32)
+    hm.hm_crc_slice(poly, sl.ctypes.data)
+    fold_t = np.zeros((4, 256), dtype=np.uint32)
+    hm.hm_crc_constmul(poly, order, hm.hm_crc_shift(poly, order, TILE - PIECE), fold_t.ctypes.data)
+    klane = [hm.hm_crc_shift(poly, order, PIECE * (31 - l)) for l in range(32)]
+    x_unit_pow = [hm.hm_crc_shift(poly, order, TILE << i) for i in range(24)]
+    x_neg_pow = [hm.hm_crc_shift(poly, order, -(1 << i)) for i in range(33)]
+    mul = lambda a, b: hm.hm_crc_mul(poly, order, a, b)   # noqa: E731
+
+    def slice4(y):
+        return int(sl[3][y & 255]) ^ int(sl[2][(y >> 8) & 255]) ^ int(sl[1][(y >> 16) & 255]) ^ int(sl[0][y >> 24])
+
+    def fold(u):
+        return int(fold_t[0][u & 255]) ^ int(fold_t[1][(u >> 8) & 255]) ^ int(fold_t[2][(u >> 16) & 255]) ^ int(fold_t[3][u >> 24])
+
+    def model(buf, a, e, T, cuts):
+        t0 = a // TILE
+        out = 0
+        bounds = [0] + sorted(cuts) + [T]
+        for lo, hi in zip(bounds[:-1], bounds[1:]):          # one warp run each
+            u = [0] * 32
+            for t in range(lo, hi):
+                for lane in range(32):
+                    col = (t0 + t) * TILE + lane * PIECE
+                    piece = bytes(buf[i] if a <= i < e else 0 for i in range(col, col + PIECE))   # masked; past the buffer: zero
+                    for w in range(0, PIECE, 4):
+                        u[lane] = slice4(u[lane] ^ int.from_bytes(piece[w:w + 4], "little"))
+                if t + 1 == hi:
+                    v = 0
+                    for lane in range(32):
+                        v ^= mul(u[lane], klane[lane])
+                    n, i = T - 1 - t, 0
+                    while n:
+                        if n & 1:
+                            v = mul(v, x_unit_pow[i])
+                        n >>= 1
+                        i += 1
+                    out ^= v                                     # atomicXor into the range's slot
+                else:
+                    u = [fold(x) for x in u]
+        z, i = (t0 + T) * TILE - e, 0
+        while z:
+            if z & 1:
+                out = mul(out, x_neg_pow[i])
+            z >>= 1
+            i += 1
+        init_term = mul(0xFFFFFFFF, hm.hm_crc_shift(poly, order, e - a))
+        return (out ^ init_term) ^ 0xFFFFFFFF
+
+    class Padded(bytes):
+        def __getitem__(self, i):
+            return bytes.__getitem__(self, i) if i < len(self) else 0
+
+    rng = np.random.default_rng(99 + pid)
+    raw = Padded(rng.integers(0, 256, 9000, dtype=np.uint8).tobytes())
+    block, stride, offset = 2996, 3000, 4                       # payload / block / header of a scaled-down crc32block image
+    T = (block + TILE - 1) // TILE + 1                          # the engine's uniform upper bound for unaligned ranges
+    for u in range(3):
+        a = offset + u * stride
+        e = min(a + block, len(raw))
+        want = oracle.crc32(bytes.__getitem__(raw, slice(a, e)), pid)
+        for cuts in ([], [1], [1, 2]):                          # whole range in one run; runs that end inside the range
+            assert model(raw, a, e, T, cuts) == want, (u, cuts)
+    # a whole 2 KiB-aligned buffer (tiles_per_range exact) and a 1-byte range
+    assert model(raw, 0, 4096, 2, [1]) == oracle.crc32(bytes.__getitem__(raw, slice(0, 4096)), pid)
+    assert model(raw, 4099, 4100, 1, []) == oracle.crc32(bytes.__getitem__(raw, slice(4099, 4100)), pid)
