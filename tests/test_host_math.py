@@ -193,3 +193,42 @@ def test_crc_flat_kernel_decomposition(hm, oracle, poly, order, pid):
     # a whole 2 KiB-aligned buffer (tiles_per_range exact) and a 1-byte range
     assert model(raw, 0, 4096, 2, [1]) == oracle.crc32(bytes.__getitem__(raw, slice(0, 4096)), pid)
     assert model(raw, 4099, 4100, 1, []) == oracle.crc32(bytes.__getitem__(raw, slice(4099, 4100)), pid)
+
+
+def test_flat_split_part_slots_bound():
+    """The flat work split of the fused kernel (bs_flat.cuh: warp g owns units [g*U/GW, (g+1)*U/GW); a run writes its CRC
+    remainder of stripe s into part slot  g - owner(first unit of s))  and the number of part slots engine.cu reserves per
+    shard (flat_geometry: (wt-1)/(U/GW) + 2, or ceil(wt*GW/U) + 2 when there are more warps than units).  Property: every
+    part index any run produces is below that bound, for batches from one stripe to thousands, ragged or not."""
+    def run_lo(g, U, GW):
+        return g * U // GW
+
+    def owner(u, U, GW):            # bsf_owner: the warp g with lo(g) <= u < lo(g+1)
+        g = u * GW // U
+        while g + 1 < GW and run_lo(g + 1, U, GW) <= u:
+            g += 1
+        while g > 0 and run_lo(g, U, GW) > u:
+            g -= 1
+        return g
+
+    rng = np.random.default_rng(2024)
+    cases = [(1, 8), (1, 171), (16, 4096), (383, 171), (1024, 171), (85, 512), (3, 1), (5000, 8), (149, 171), (2, 100000)]
+    cases += [(int(rng.integers(1, 3000)), int(rng.integers(1, 600))) for _ in range(40)]
+    for n_stripes, wt in cases:
+        nw = 12                                                   # 384 threads
+        U = n_stripes * wt
+        grid = max(1, min((U + nw - 1) // nw, 148))
+        GW = grid * nw
+        max_parts = (wt - 1) // (U // GW) + 2 if U >= GW else (wt * GW + U - 1) // U + 2
+        worst = 0
+        for g in range(GW):
+            lo, hi = run_lo(g, U, GW), run_lo(g + 1, U, GW)
+            assert 0 <= hi - lo <= U // GW + 1
+            if lo == hi:
+                continue
+            assert owner(lo, U, GW) == g and owner(hi - 1, U, GW) == g
+            for s in range(lo // wt, (hi - 1) // wt + 1):        # every stripe this run touches
+                part = g - owner(s * wt, U, GW)
+                assert 0 <= part < max_parts, (n_stripes, wt, g, s, part, max_parts)
+                worst = max(worst, part + 1)
+        assert worst >= 1
