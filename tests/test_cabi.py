@@ -85,3 +85,24 @@ def test_runtime_codegen_compiles_for_every_erasure_class(cb):
     pres = np.ones(6, np.uint8)
     pres[[0, 1, 2]] = 0
     assert L.cubeec_debug_jit_check(4, 2, pres.ctypes.data, 0, None, 0) == 3
+
+
+def test_crc32block_size_math_without_gpu(cb):
+    """crc32block.EncodeSize / DecodeSize (blobstore/common/crc32block/util.go:56-71) are host arithmetic in the ABI:
+    size + 4 * ceil(size / (blockLen - 4)) and back; blockLen must be a positive multiple of 4096 (isValidBlockLen,
+    util.go:40-42; the reference panics with ErrInvalidBlock), else 0.  The on-disk sizes the reference's tests pin (datafile_test.go:194-195,237-241: a
+    9-byte shard occupies 32 + 9 + 4 + 8 bytes) follow from it."""
+    L = cb.load()
+    L.cubeec_crc32block_encode_size.restype = ctypes.c_size_t
+    L.cubeec_crc32block_encode_size.argtypes = [ctypes.c_size_t, ctypes.c_size_t]
+    L.cubeec_crc32block_decode_size.restype = ctypes.c_size_t
+    L.cubeec_crc32block_decode_size.argtypes = [ctypes.c_size_t, ctypes.c_size_t]
+    for block in (4096, 8192, 65536, 1 << 20):
+        payload = block - 4
+        for n in (0, 1, 9, payload - 1, payload, payload + 1, 2 * payload, 2 * payload + 1, 349526, (1 << 22) + 5, 1 << 30):
+            enc = L.cubeec_crc32block_encode_size(n, block)
+            assert enc == n + 4 * ((n + payload - 1) // payload), (block, n)
+            assert L.cubeec_crc32block_decode_size(enc, block) == n, (block, n)
+    assert L.cubeec_crc32block_encode_size(9, 65536) == 13          # 32-byte header + 13 + 8-byte footer = the 53 bytes on disk
+    for bad in (0, 1000, 4095, 4097, 65536 + 4):
+        assert L.cubeec_crc32block_encode_size(100, bad) == 0 and L.cubeec_crc32block_decode_size(100, bad) == 0
